@@ -1,0 +1,169 @@
+/*
+ * mvus_ba.h -- C ABI of the B200-native bundle-adjustment path for mvus.
+ *
+ * The reference (CenekAlbl/mvus) is pure Python and has NO foreign-function interface;
+ * this header is the boundary a maintainer binds from Python (ctypes, see
+ * INTEGRATION.md) to replace the body of
+ *
+ *     Scene.BA(numCam, max_iter, rs, motion_prior, motion_reg, motion_weights, norm,
+ *              rs_bounds)                     multiviewunsynch/reconstruction/common.py:441-697
+ *
+ * Every entry point cites the reference lines it replaces.  Conventions:
+ *   - plain C, FP64 throughout (the reference is NumPy float64 end to end);
+ *   - all array arguments are HOST pointers unless the name ends in _dev; the handle owns
+ *     all device memory, the caller owns all host memory;
+ *   - every function returns 0 on success and a negative mvus_status on error;
+ *     mvus_ba_last_error() gives the message.  No exceptions cross the ABI;
+ *   - one handle = one CUDA device + one stream; a handle is not thread-safe, distinct
+ *     handles are independent;
+ *   - there is NO CPU fallback: without a usable CUDA device mvus_ba_create fails with
+ *     MVUS_ERR_CUDA.
+ *
+ * Parameter vector x (length n), exactly the reference layout (common.py:616-650):
+ *   [ alpha(nc) | beta(nc) | rho(nc) | cam_0 .. cam_{nc-1} | spline_0: cx|cy|cz | spline_1 .. ]
+ *   cam_i = [rvec(3), t(3)]                         (6)   opt_calib = 0   common.py:1124
+ *         = [fx, fy, cx, cy, rvec(3), t(3), d(5)]   (15)  opt_calib = 1   common.py:1122
+ * Residual vector r (length m), exactly the reference order (common.py:476-487, 359):
+ *   for each camera i: [ |e_u| (N_i) , |e_v| (N_i) ], then the M motion-prior rows.
+ */
+#ifndef MVUS_BA_H
+#define MVUS_BA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mvus_ba_ctx* mvus_ba_handle;
+
+enum mvus_status {
+    MVUS_OK = 0,
+    MVUS_ERR_ARG = -1,       /* bad argument / call order */
+    MVUS_ERR_CUDA = -2,      /* CUDA runtime error or no device */
+    MVUS_ERR_NONFINITE = -3, /* "Residuals are not finite in the initial point." (scipy least_squares.py:945) */
+    MVUS_ERR_UNSUPPORTED = -4,
+    MVUS_ERR_NCCL = -5
+};
+
+enum mvus_motion_type { MVUS_MOTION_NONE = 0, MVUS_MOTION_F = 1, MVUS_MOTION_KE = 2 };
+
+/* Problem description: what Scene.BA reads from its arguments and self.settings
+ * (common.py:441, 454-460, 512-525, 621, 655-662; main.py:49-52). */
+typedef struct mvus_ba_desc {
+    int32_t num_cams;        /* numCam                                                   */
+    int32_t opt_calib;       /* settings['opt_calib']  -> 15 instead of 6 camera unknowns */
+    int32_t undist_points;   /* settings['undist_points'] (common.py:126)                */
+    int32_t opt_sync;        /* settings.get('opt_sync', True): alpha/beta free (512-515) */
+    int32_t opt_rs;          /* BA(rs=...): rho free (518-521)                            */
+    int32_t rs_bounds;       /* BA(rs_bounds=...): rho in [0,1] (655-660)                 */
+    int32_t motion_type;     /* mvus_motion_type; NONE when motion_reg is False           */
+    int32_t device;          /* CUDA device ordinal                                       */
+    double  motion_weight;   /* motion_weights (483-485)                                  */
+    int32_t max_nfev;        /* max_iter -> least_squares(max_nfev=...) (670)             */
+    int32_t reserved0;
+    double  ftol, xtol, gtol;/* SciPy defaults 1e-8 / reference xtol=1e-12 / 1e-8 (670)   */
+} mvus_ba_desc;
+
+/* What scipy's OptimizeResult carries back (common.py:697) plus timing. */
+typedef struct mvus_ba_stats {
+    double  cost0;           /* 0.5*|r(x0)|^2                                             */
+    double  cost;            /* 0.5*|r(x*)|^2                                             */
+    double  optimality;      /* |J^T r|_inf at x*                                         */
+    double  lambda;          /* final LM damping                                          */
+    int32_t nfev;            /* residual evaluations                                      */
+    int32_t njev;            /* Jacobian evaluations                                      */
+    int32_t status;          /* 0 max_nfev, 1 gtol, 2 ftol, 3 xtol, 4 ftol&xtol (scipy codes); -1 failure */
+    int32_t lm_iterations;   /* accepted + rejected linear solves                         */
+    double  ms_total;        /* device time of the whole solve (CUDA events)              */
+    double  ms_resjac;       /* summed device time in K1/K1m with Jacobian                */
+    double  ms_accum;        /* summed device time in K2/K2m                              */
+    double  ms_solve;        /* summed device time in the Schur/Cholesky step             */
+    double  ms_trial;        /* summed device time in residual-only evaluations           */
+    int32_t launches;        /* kernels launched by this library during the solve         */
+    int32_t n_resjac;        /* number of K1(with J) launches timed in ms_resjac          */
+} mvus_ba_stats;
+
+const char* mvus_ba_version(void);
+
+/* Create / destroy a problem handle.  Replaces nothing in the reference by itself; holds
+ * what common.py:612-665 derives from the Scene. */
+int  mvus_ba_create(const mvus_ba_desc* desc, mvus_ba_handle* out);
+void mvus_ba_destroy(mvus_ba_handle h);
+const char* mvus_ba_last_error(mvus_ba_handle h);   /* h may be NULL: last create error */
+
+/* Detections of the nc optimised cameras, concatenated in sequence order.
+ * cam_ptr[nc+1]: offsets; frame/x/y: rows 0/1/2 of Scene.detections[i] (common.py:1190,
+ * sorted by frame); height[i] = cameras[i].resolution[1] (common.py:125).
+ * calib: nc x 9 = (fx, fy, cx, cy, k1, k2, p1, p2, k3) -- used as constants when
+ * opt_calib = 0 (common.py:126, 1147-1157) and ignored otherwise. */
+int mvus_ba_set_detections(mvus_ba_handle h, const int64_t* cam_ptr, const double* frame,
+                           const double* x, const double* y, const double* height,
+                           const double* calib);
+
+/* Splines: Scene.spline['tck'] / ['int'] (common.py:224-270).  interval: 2*S doubles
+ * (row 0 = starts, row 1 = ends, i.e. the 2 x S array flattened); knot_ptr[S+1] into
+ * knots[]; degree[s] in {1,3} (common.py:247, 267).  Coefficients travel inside x. */
+int mvus_ba_set_splines(mvus_ba_handle h, int32_t num_splines, const double* interval,
+                        const int64_t* knot_ptr, const double* knots, const int32_t* degree);
+
+/* Problem sizes after the two setters: n = len(x), m = len(r), N detections, M motion
+ * rows, P = 3 + C + 12 compact Jacobian columns per detection row. */
+int mvus_ba_dims(mvus_ba_handle h, int64_t* n, int64_t* m, int64_t* N, int64_t* M, int32_t* P);
+
+/* r = error_BA(x)   (common.py:448-487).  x, r host pointers. */
+int mvus_ba_residual(mvus_ba_handle h, const double* x, double* r);
+
+/* r and the analytic Jacobian of error_BA at x -- replaces the (1 + n_groups) finite
+ * difference evaluations scipy does per Jacobian (scipy/optimize/_numdiff.py:770-895) and
+ * the pattern of jac_BA (common.py:490-610).  Compact block-row form:
+ *   span[N]     : global index of the LAST active control point of the detection
+ *                 (control points are numbered consecutively over the splines), -1 if the
+ *                 detection is covered by no interval (row is zero, common.py:565-566);
+ *   J[2*P*N]    : column planes, J[p*N + d] = d|e_u|(d)/d q_p and J[(P+p)*N + d] for e_v,
+ *                 q = (alpha_i, beta_i, rho_i, cam_i (C), then 4 control points
+ *                 span-3..span, each (x, y, z));
+ *   mbase[M]    : first control point touched by motion row j, -1 if the row is zero;
+ *   mJ[10*M]    : planes; axis factors a[0..2] then control-point factors c[0..6]:
+ *                 d r_j / d C_{mbase+k, axis} = a[axis] * c[k].
+ * Any of span/J/mbase/mJ may be NULL. */
+int mvus_ba_residual_jacobian(mvus_ba_handle h, const double* x, double* r, int32_t* span,
+                              double* J, int32_t* mbase, double* mJ);
+
+/* Full solve: replaces least_squares(error_BA, x0, jac_sparsity=A, tr_solver='lsmr',
+ * xtol=1e-12, max_nfev=max_iter, bounds=...) (common.py:670) -- Levenberg-Marquardt with
+ * exact steps from the Schur-reduced normal equations.  x0 in, x* out (host, length n);
+ * r_out (length m, may be NULL) receives error_BA(x*). */
+int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, double* r_out,
+                  mvus_ba_stats* stats);
+
+/* detections_global of the optimised cameras at parameters x (common.py:105-127, 695):
+ * t = alpha (f + rho y/H) + beta and the (undistorted) observation; each output N long. */
+int mvus_ba_detections_global(mvus_ba_handle h, const double* x, double* t, double* u, double* v);
+
+/* Diagnostics used by the parity tests: the normal equations K2 assembles at x.
+ *   A    [nc*Pc*Pc]  camera diagonal blocks (Pc = 3 + C), row-major per camera
+ *   g    [n]         J^T r in the reference's x layout
+ *   Hss  : spline-spline block returned as a dense band: for control points i <= j <
+ *          i + bw (bw = *band_ctrl), Hss[((i*bw)+(j-i))*9 + a*3 + b]
+ *   Hcs  [nc*Pc * 3*n_ctrl] camera x spline coupling, row-major, spline column = 3*j+axis
+ * Any output may be NULL. */
+int mvus_ba_normal_equations(mvus_ba_handle h, const double* x, double* A, double* g,
+                             double* Hss, int32_t* band_ctrl, double* Hcs, double* cost);
+
+/* Multi-GPU (one process per GPU): join an NCCL communicator whose unique id was
+ * produced by mvus_ba_nccl_unique_id on rank 0 and broadcast by the host framework
+ * (torch.distributed).  After this, detections set on each rank are that rank's shard
+ * and the normal equations are summed over ranks. */
+int mvus_ba_nccl_unique_id(char id_out[128]);
+int mvus_ba_comm_init(mvus_ba_handle h, int32_t world_size, int32_t rank, const char id[128]);
+
+/* Timing helper for benchmarks: run `reps` back-to-back residual+Jacobian evaluations
+ * (K1 + K1m) at x on the handle's stream, return the mean device ms (CUDA events). */
+int mvus_ba_time_resjac(mvus_ba_handle h, const double* x, int32_t reps, double* ms_mean);
+int mvus_ba_time_accumulate(mvus_ba_handle h, int32_t reps, double* ms_mean);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVUS_BA_H */

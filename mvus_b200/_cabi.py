@@ -1,0 +1,202 @@
+"""ctypes binding of libmvus_ba.so (include/mvus_ba.h).  There is NO fallback: if the CUDA
+library is missing or no GPU is usable, every call raises."""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libmvus_ba.so')
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int32)
+_lp = ctypes.POINTER(ctypes.c_int64)
+
+
+class BADesc(ctypes.Structure):
+    _fields_ = [('num_cams', ctypes.c_int32), ('opt_calib', ctypes.c_int32),
+                ('undist_points', ctypes.c_int32), ('opt_sync', ctypes.c_int32),
+                ('opt_rs', ctypes.c_int32), ('rs_bounds', ctypes.c_int32),
+                ('motion_type', ctypes.c_int32), ('device', ctypes.c_int32),
+                ('motion_weight', ctypes.c_double), ('max_nfev', ctypes.c_int32),
+                ('reserved0', ctypes.c_int32), ('ftol', ctypes.c_double), ('xtol', ctypes.c_double),
+                ('gtol', ctypes.c_double)]
+
+
+class BAStats(ctypes.Structure):
+    _fields_ = [('cost0', ctypes.c_double), ('cost', ctypes.c_double), ('optimality', ctypes.c_double),
+                ('lam', ctypes.c_double), ('nfev', ctypes.c_int32), ('njev', ctypes.c_int32),
+                ('status', ctypes.c_int32), ('lm_iterations', ctypes.c_int32),
+                ('ms_total', ctypes.c_double), ('ms_resjac', ctypes.c_double),
+                ('ms_accum', ctypes.c_double), ('ms_solve', ctypes.c_double),
+                ('ms_trial', ctypes.c_double), ('launches', ctypes.c_int32), ('n_resjac', ctypes.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = ['mvus_ba_version', 'mvus_ba_create', 'mvus_ba_destroy', 'mvus_ba_last_error',
+           'mvus_ba_set_detections', 'mvus_ba_set_splines', 'mvus_ba_dims', 'mvus_ba_residual',
+           'mvus_ba_residual_jacobian', 'mvus_ba_solve', 'mvus_ba_detections_global',
+           'mvus_ba_normal_equations', 'mvus_ba_nccl_unique_id', 'mvus_ba_comm_init',
+           'mvus_ba_time_resjac', 'mvus_ba_time_accumulate']
+
+_lib = None
+
+
+class MvusError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; raises if it has not been built (no CPU path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MvusError('%s not built: run `python -m mvus_b200.build` (the BA path has no CPU fallback)'
+                        % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.mvus_ba_version.restype = ctypes.c_char_p
+    lib.mvus_ba_last_error.restype = ctypes.c_char_p
+    lib.mvus_ba_last_error.argtypes = [ctypes.c_void_p]
+    lib.mvus_ba_create.argtypes = [ctypes.POINTER(BADesc), ctypes.POINTER(ctypes.c_void_p)]
+    lib.mvus_ba_destroy.argtypes = [ctypes.c_void_p]
+    lib.mvus_ba_destroy.restype = None
+    lib.mvus_ba_set_detections.argtypes = [ctypes.c_void_p, _lp, _dp, _dp, _dp, _dp, _dp]
+    lib.mvus_ba_set_splines.argtypes = [ctypes.c_void_p, ctypes.c_int32, _dp, _lp, _dp, _ip]
+    lib.mvus_ba_dims.argtypes = [ctypes.c_void_p, _lp, _lp, _lp, _lp, _ip]
+    lib.mvus_ba_residual.argtypes = [ctypes.c_void_p, _dp, _dp]
+    lib.mvus_ba_residual_jacobian.argtypes = [ctypes.c_void_p, _dp, _dp, _ip, _dp, _ip, _dp]
+    lib.mvus_ba_solve.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, ctypes.POINTER(BAStats)]
+    lib.mvus_ba_detections_global.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp]
+    lib.mvus_ba_normal_equations.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp, _ip, _dp, _dp]
+    lib.mvus_ba_nccl_unique_id.argtypes = [ctypes.c_char_p]
+    lib.mvus_ba_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p]
+    lib.mvus_ba_time_resjac.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int32, _dp]
+    lib.mvus_ba_time_accumulate.argtypes = [ctypes.c_void_p, ctypes.c_int32, _dp]
+    _lib = lib
+    return lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip) if a is not None else None
+
+
+def _l(a):
+    return a.ctypes.data_as(_lp)
+
+
+class Handle:
+    """One BA problem on one GPU (wraps mvus_ba_handle)."""
+
+    def __init__(self, fp, device=0, ftol=1e-8, xtol=1e-12, gtol=1e-8, max_nfev=None):
+        self.lib = load()
+        self.fp = fp
+        desc = BADesc(num_cams=fp.nc, opt_calib=int(fp.opt_calib), undist_points=int(fp.undist),
+                      opt_sync=int(fp.opt_sync), opt_rs=int(fp.opt_rs), rs_bounds=int(fp.rs_bounds),
+                      motion_type=int(fp.motion_type), device=int(device),
+                      motion_weight=float(fp.motion_weight),
+                      max_nfev=int(fp.max_nfev if max_nfev is None else max_nfev), reserved0=0,
+                      ftol=ftol, xtol=xtol, gtol=gtol)
+        self.h = ctypes.c_void_p()
+        rc = self.lib.mvus_ba_create(ctypes.byref(desc), ctypes.byref(self.h))
+        if rc != 0:
+            raise MvusError('mvus_ba_create: %s' % self.lib.mvus_ba_last_error(None).decode())
+        self._check(self.lib.mvus_ba_set_detections(self.h, _l(fp.cam_ptr), _d(fp.frame), _d(fp.x_raw),
+                                                    _d(fp.y_raw), _d(fp.height), _d(fp.calib)))
+        interval = np.ascontiguousarray(fp.interval.reshape(-1))
+        self._check(self.lib.mvus_ba_set_splines(self.h, fp.S, _d(interval), _l(fp.knot_ptr), _d(fp.knots),
+                                                 _i(fp.degree)))
+        n, m, N, M = (ctypes.c_int64() for _ in range(4))
+        P = ctypes.c_int32()
+        self._check(self.lib.mvus_ba_dims(self.h, ctypes.byref(n), ctypes.byref(m), ctypes.byref(N),
+                                          ctypes.byref(M), ctypes.byref(P)))
+        self.n, self.m, self.N, self.M, self.P = n.value, m.value, N.value, M.value, P.value
+        assert self.n == fp.n, (self.n, fp.n)
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.mvus_ba_last_error(self.h).decode()
+            if rc == -3:
+                raise ValueError(msg)       # scipy raises ValueError here too (least_squares.py:945)
+            raise MvusError('mvus_ba error %d: %s' % (rc, msg))
+
+    def close(self):
+        if self.h:
+            self.lib.mvus_ba_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def comm_init(self, world, rank, uid):
+        self._check(self.lib.mvus_ba_comm_init(self.h, world, rank, uid))
+
+    def residual(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        r = np.empty(self.m)
+        self._check(self.lib.mvus_ba_residual(self.h, _d(x), _d(r)))
+        return r
+
+    def residual_jacobian(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        r = np.empty(self.m)
+        span = np.empty(self.N, dtype=np.int32)
+        J = np.empty(2 * self.P * self.N)
+        mbase = np.empty(self.M, dtype=np.int32)
+        mJ = np.empty(10 * self.M)
+        self._check(self.lib.mvus_ba_residual_jacobian(self.h, _d(x), _d(r), _i(span), _d(J), _i(mbase), _d(mJ)))
+        return r, span, J, mbase, mJ
+
+    def solve(self, x0, want_r=True):
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        x = np.empty(self.n)
+        r = np.empty(self.m) if want_r else None
+        st = BAStats()
+        self._check(self.lib.mvus_ba_solve(self.h, _d(x0), _d(x), _d(r), ctypes.byref(st)))
+        return x, r, st
+
+    def detections_global(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        t, u, v = np.empty(self.N), np.empty(self.N), np.empty(self.N)
+        self._check(self.lib.mvus_ba_detections_global(self.h, _d(x), _d(t), _d(u), _d(v)))
+        return t, u, v
+
+    def normal_equations(self, x, want_dense=True):
+        fp = self.fp
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        A = np.empty(fp.nc * fp.Pc * fp.Pc)
+        g = np.empty(self.n)
+        band = ctypes.c_int32()
+        cost = ctypes.c_double()
+        # first call to learn the band width
+        self._check(self.lib.mvus_ba_normal_equations(self.h, _d(x), _d(A), _d(g), None, ctypes.byref(band),
+                                                      None, ctypes.byref(cost)))
+        Hss = Hcs = None
+        if want_dense:
+            Hss = np.empty(fp.n_ctrl * band.value * 9)
+            Hcs = np.empty(fp.nc * fp.Pc * 3 * fp.n_ctrl)
+            self._check(self.lib.mvus_ba_normal_equations(self.h, _d(x), _d(A), _d(g), _d(Hss),
+                                                          ctypes.byref(band), _d(Hcs), ctypes.byref(cost)))
+            Hss = Hss.reshape(fp.n_ctrl, band.value, 3, 3)
+            Hcs = Hcs.reshape(fp.nc * fp.Pc, 3 * fp.n_ctrl)
+        return A.reshape(fp.nc, fp.Pc, fp.Pc), g, Hss, Hcs, cost.value
+
+    def time_resjac(self, x, reps=5):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        ms = ctypes.c_double()
+        self._check(self.lib.mvus_ba_time_resjac(self.h, _d(x), reps, ctypes.byref(ms)))
+        return ms.value
+
+    def time_accumulate(self, reps=5):
+        ms = ctypes.c_double()
+        self._check(self.lib.mvus_ba_time_accumulate(self.h, reps, ctypes.byref(ms)))
+        return ms.value

@@ -1,0 +1,239 @@
+"""Drop-in bundle adjustment: the reference's ``Scene.BA`` (reconstruction/common.py:441-697)
+with the whole inner loop on the GPU.
+
+``bundle_adjust(scene, numCam, ...)`` keeps the reference signature, reads the same Scene
+attributes and leaves the same post-conditions:
+  * alpha/beta/rs[sequence[:nc]] updated (common.py:676)
+  * cameras: R, t (and K, d under opt_calib) set, P recomposed (common.py:678-680, 1143)
+  * spline['tck'][s][1] = [cx, cy, cz] (common.py:689-692)
+  * detections_global refreshed for ALL cameras (common.py:695)
+  * visible set from the PRE-BA parameters (common.py:493 -> compute_visibility)
+  * under motion_reg: traj = unit-step samples and the global_* bookkeeping arrays
+    (common.py:464, 630, 887-944) -- they are pickled outputs (README.md:216-221)
+and returns a scipy-style OptimizeResult.
+
+Every per-detection computation goes through the C ABI (mvus_b200/_cabi.py ->
+libmvus_ba.so).  If that library is missing or there is no GPU this module raises; there is
+no CPU path.
+"""
+import numpy as np
+
+from . import _cabi
+from .problem import FlatProblem
+
+try:                                       # scipy's result container, when available
+    from scipy.optimize import OptimizeResult
+except Exception:                          # pragma: no cover
+    class OptimizeResult(dict):
+        __getattr__ = dict.get
+        __setattr__ = dict.__setitem__
+
+_MESSAGES = {-1: 'Linear solve failed (normal matrix not positive definite at maximum damping).',
+             0: 'The maximum number of function evaluations is exceeded.',
+             1: '`gtol` termination condition is satisfied.',
+             2: '`ftol` termination condition is satisfied.',
+             3: '`xtol` termination condition is satisfied.',
+             4: 'Both `ftol` and `xtol` termination conditions are satisfied.'}
+
+DEVICE = 0
+_COMM = None          # (world, rank, uid bytes) set by mvus_b200.shard.init_comm
+
+
+def _all_cams_problem(scene):
+    """A FlatProblem over ALL cameras (used for detections_global / visibility refresh)."""
+    class _S:
+        pass
+    s = _S()
+    s.__dict__.update({k: getattr(scene, k) for k in ('settings', 'cameras', 'detections', 'alpha', 'beta',
+                                                     'rs', 'spline')})
+    s.sequence = list(range(scene.numCam))
+    return FlatProblem(s, scene.numCam)
+
+
+def _interval_membership(t, interval):
+    """util.sampling(..., belong=True) index (util.py:103-106) for already-computed times."""
+    idx = np.zeros(len(t), dtype=int)
+    for s in range(interval.shape[1]):
+        mask = np.logical_xor(t - interval[0, s] >= 0, t - interval[1, s] >= 0)
+        idx[mask] = s + 1
+    return idx
+
+
+def detection_to_global(scene, *cam, motion_prior=False):
+    """Scene.detection_to_global (common.py:105-127): global time stamps and (undistorted)
+    observations, computed by the library's det_global kernel."""
+    if motion_prior:
+        raise NotImplementedError('motion_prior=True (discrete-trajectory mode) is not part of the BA path '
+                                  'main.py uses; see SURVEY.md 8b / 8f')
+    assert len(scene.alpha) == scene.numCam and len(scene.beta) == scene.numCam, \
+        'The Number of alpha and beta is wrong'
+    if len(cam):
+        cams = cam
+        if not isinstance(cams[0], (int, np.integer)):
+            cams = cams[0]
+        cams = [int(c) for c in cams]
+    else:
+        cams = list(range(scene.numCam))
+        scene.detections_global = [[] for _ in cams]
+
+    class _S:
+        pass
+    s = _S()
+    s.__dict__.update({k: getattr(scene, k) for k in ('settings', 'cameras', 'detections', 'alpha', 'beta',
+                                                     'rs', 'spline')})
+    s.sequence = cams
+    fp = FlatProblem(s, len(cams))
+    hd = _cabi.Handle(fp, device=DEVICE)
+    try:
+        t, u, v = hd.detections_global(fp.x0)
+    finally:
+        hd.close()
+    while len(scene.detections_global) < scene.numCam:
+        scene.detections_global.append([])
+    for k, i in enumerate(cams):
+        a, b = fp.cam_ptr[k], fp.cam_ptr[k + 1]
+        scene.detections_global[i] = np.vstack((t[a:b], u[a:b], v[a:b]))
+
+
+def compute_visibility(scene):
+    """Scene.compute_visibility (common.py:427-438)."""
+    detection_to_global(scene)
+    interval = np.asarray(scene.spline['int'], dtype=np.float64)
+    scene.visible = [_interval_membership(scene.detections_global[i][0], interval)
+                     for i in range(scene.numCam)]
+
+
+def error_cam(scene, cam_id, mode='dist', motion_prior=False, norm=False):
+    """Scene.error_cam (common.py:304-359) through the residual kernel.  Modes as in the
+    reference; 'each' keeps zeros for uncovered detections, the others drop them."""
+    if motion_prior or norm:
+        raise NotImplementedError('error_cam(motion_prior/norm=True) is outside the BA path (SURVEY.md 8f)')
+
+    class _S:
+        pass
+    s = _S()
+    s.__dict__.update({k: getattr(scene, k) for k in ('settings', 'cameras', 'detections', 'alpha', 'beta',
+                                                     'rs', 'spline')})
+    s.sequence = [int(cam_id)]
+    fp = FlatProblem(s, 1)
+    hd = _cabi.Handle(fp, device=DEVICE)
+    try:
+        r, span, _, _, _ = hd.residual_jacobian(fp.x0)
+        t, u, v = hd.detections_global(fp.x0)
+    finally:
+        hd.close()
+    scene.detections_global[cam_id] = np.vstack((t, u, v))
+    N = fp.N
+    eu, ev = r[:N], r[N:2 * N]
+    if mode == 'each':
+        return np.concatenate((eu, ev))
+    cov = span >= 0
+    # the reference concatenates interval by interval; detections are time-sorted so this is the same order
+    if mode == 'dist':
+        return np.sqrt(eu[cov] ** 2 + ev[cov] ** 2)
+    if mode == 'xy_1D':
+        return np.concatenate((eu[cov], ev[cov]))
+    if mode == 'xy_2D':
+        return np.vstack((eu[cov], ev[cov]))
+    raise ValueError('unknown mode %r' % (mode,))
+
+
+def remove_outliers(scene, cams, thres=30, verbose=False):
+    """Scene.remove_outliers (common.py:700-717)."""
+    if not thres:
+        return
+    for i in cams:
+        e = error_cam(scene, i, mode='each')
+        ex, ey = np.split(e, 2)
+        err = np.sqrt(ex ** 2 + ey ** 2)
+        scene.detections[i] = scene.detections[i][:, err < thres]
+        detection_to_global(scene, i)
+        if verbose:
+            print('{} out of {} detections are removed for camera {}'.format(
+                int(np.sum(err >= thres)), int(np.sum(err != 0)), i))
+
+
+def _bspline_eval(t, tck):
+    """splev(t, tck) for the bookkeeping outputs (traj); scipy when present."""
+    from scipy import interpolate
+    return np.asarray(interpolate.splev(t, tck))
+
+
+def spline_to_traj(scene, sampling_rate=1, t=None):
+    """Scene.spline_to_traj (common.py:273-301): host-side bookkeeping output (pickled
+    ``traj``); not part of the residual evaluation, which samples on the device."""
+    tck, interval = scene.spline['tck'], np.asarray(scene.spline['int'])
+    scene.traj = np.empty([4, 0])
+    if t is not None:
+        assert len(t.shape) == 1, 'Input timestamps must be a 1D array'
+        timestamp = t
+    else:
+        timestamp = np.arange(interval[0, 0], interval[1, -1], sampling_rate)
+    for i in range(interval.shape[1]):
+        t_part = timestamp[np.logical_and(timestamp >= interval[0, i], timestamp <= interval[1, i])]
+        try:
+            part = _bspline_eval(t_part, tck[i])
+        except Exception:
+            continue
+        scene.traj = np.hstack((scene.traj, np.vstack((t_part, part))))
+    assert (scene.traj[0, 1:] >= scene.traj[0, :-1]).all()
+    return scene.traj
+
+
+def _all_detect_to_traj(scene, cams):
+    """Bookkeeping of Scene.all_detect_to_traj (common.py:887-944) from refreshed
+    detections_global: global_time_stamps_all, frame_id_all, global_detections, global_traj."""
+    ts = np.concatenate([scene.detections_global[i][0] for i in cams])
+    fid = np.concatenate([np.asarray(scene.detections[i][0], dtype=np.float64) for i in cams])
+    cid = np.concatenate([np.ones(scene.detections[i].shape[1]) * i for i in cams])
+    scene.frame_id_all = fid
+    scene.global_time_stamps_all = ts
+    traj = spline_to_traj(scene, t=np.sort(ts))
+    scene.global_detections = np.vstack((cid, fid, ts))
+    tmp = scene.global_detections[:, np.argsort(scene.global_detections[2, :])]
+    keep = np.isin(tmp[2], traj[0])
+    tmp = np.vstack((tmp[:, keep], traj[1:]))
+    scene.global_traj = np.vstack((np.arange(tmp.shape[1]), tmp))
+
+
+def bundle_adjust(scene, numCam, max_iter=10, rs=False, motion_prior=False, motion_reg=False,
+                  motion_weights=1, norm=False, rs_bounds=False, ftol=1e-8, xtol=1e-12, gtol=1e-8,
+                  return_handle=False):
+    """Scene.BA(numCam, max_iter, rs, motion_prior, motion_reg, motion_weights, norm, rs_bounds)
+    -- reference signature (common.py:441); ``max_iter`` is scipy's max_nfev (common.py:670),
+    xtol = 1e-12 as the reference passes, ftol / gtol = scipy defaults."""
+    if motion_prior:
+        raise NotImplementedError('BA(motion_prior=True) (discrete-trajectory mode, common.py:466-467) is '
+                                  'never used by main.py and is not implemented; see SURVEY.md 8b')
+    fp = FlatProblem(scene, numCam, rs=rs, motion_reg=motion_reg, motion_weights=motion_weights,
+                     rs_bounds=rs_bounds, max_iter=max_iter)
+    print('Number of BA parameters is {}'.format(fp.n))
+
+    # visibility with PRE-BA parameters (common.py:493)
+    compute_visibility(scene)
+
+    print('Doing BA with {} cameras...\n'.format(numCam))
+    hd = _cabi.Handle(fp, device=DEVICE, ftol=ftol, xtol=xtol, gtol=gtol)
+    try:
+        if _COMM is not None and _COMM[0] > 1:
+            hd.comm_init(*_COMM)
+        x, r, st = hd.solve(fp.x0)
+    finally:
+        if not return_handle:
+            hd.close()
+
+    fp.unpack_into(scene, x)
+    detection_to_global(scene)
+    if motion_reg:
+        spline_to_traj(scene)                      # common.py:379 leaves traj = unit-step samples
+        unit_traj = scene.traj
+        _all_detect_to_traj(scene, fp.seq)
+        scene.traj = unit_traj
+
+    res = OptimizeResult(x=x, cost=st.cost, fun=r, jac=None, grad=None, optimality=st.optimality,
+                         active_mask=np.zeros(fp.n, dtype=int), nfev=st.nfev, njev=st.njev,
+                         status=st.status, message=_MESSAGES.get(st.status, ''), success=st.status > 0)
+    res.stats = st.as_dict()
+    if return_handle:
+        res.handle = hd
+    return res

@@ -1,0 +1,113 @@
+// Context (handle) of the BA library, device-buffer helpers and error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/mvus_ba.h"
+#include "ba_math.cuh"
+#include "ba_tables.hpp"
+
+namespace mvus {
+
+constexpr int TILE_DET = 128;      // detections per CTA tile (one camera per tile)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+struct NcclApi;   // ba_nccl.cuh
+
+}  // namespace mvus
+
+struct mvus_ba_ctx {
+    mvus_ba_desc desc;
+    std::string err;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int sm_count = 148;
+
+    // sizes
+    int nc = 0, C = 6, Pc = 9, P = 21;
+    int64_t N = 0, M = 0, n = 0, m = 0, n_other = 0, n_ctrl = 0;
+    bool have_det = false, have_spl = false;
+
+    // detections
+    std::vector<int64_t> cam_ptr;
+    mvus::DevBuf<double> frame, xr, yr, obs_u, obs_v, calib, height;
+    mvus::DevBuf<int64_t> row_off;
+    int n_tiles = 0;
+    mvus::DevBuf<int> tile_cam, tile_cnt;
+    mvus::DevBuf<int64_t> tile_start;
+
+    // splines (static tables)
+    mvus::HostSplineTables T;
+    mvus::DevBuf<double> int_a, int_b, knots, spanpoly, span_t0, lut_t0, lut_invh;
+    mvus::DevBuf<int64_t> knot_off, ctrl_off, xoff, lut_off;
+    mvus::DevBuf<int> ncoef, deg, lut_n, lut;
+    mvus::SplineView sv;
+
+    // motion samples
+    mvus::DevBuf<double> tau;
+    mvus::DevBuf<int> tau_spl;
+    mvus::DevBuf<unsigned char> tau_flag;
+
+    // per-evaluation state
+    mvus::DevBuf<double> x, x_trial, camprep, r, J, mJ, partial;
+    mvus::DevBuf<int> span, mbase, flag;
+    double* h_pin = nullptr;      // pinned scratch for scalars
+    size_t h_pin_n = 0;
+
+    // normal equations / solver (ba_solve.cuh)
+    int bw = 3, q = 9;            // control points per super-block, unknowns per super-block
+    int64_t nb = 0;               // super-blocks
+    int ncP = 0, ldw = 0;         // camera unknowns, leading dimension of W~ (ncP + 1 rhs column)
+    mvus::DevBuf<double> A, D, E, W, Dw, Ew, Ww, ZL, Sd, dlt_c, dlt_s, diag_c, diag_s, gvec, xs;
+    int launches = 0;
+    int64_t cost_slot = 0;        // index in `partial` where the last evaluation left sum r^2
+
+    // multi-GPU
+    int world = 1, rank = 0;
+    void* nccl_comm = nullptr;
+};
+
+namespace mvus {
+
+inline int fail(mvus_ba_ctx* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+#define MV_CUDA(h, call)                                                                      \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return mvus::fail(h, MVUS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+template <class T>
+inline cudaError_t upload(DevBuf<T>& b, const T* src, size_t n, cudaStream_t st) {
+    cudaError_t e = b.alloc(n > 0 ? n : 1);
+    if (e != cudaSuccess || n == 0) return e;
+    return cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st);
+}
+template <class T>
+inline cudaError_t upload(DevBuf<T>& b, const std::vector<T>& v, cudaStream_t st) {
+    return upload(b, v.data(), v.size(), st);
+}
+
+}  // namespace mvus

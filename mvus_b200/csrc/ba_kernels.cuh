@@ -1,0 +1,186 @@
+// K0 / K1 / K1m: camera preparation, fused residual + analytic Jacobian per detection,
+// motion-prior rows.  One thread per detection (per motion sample); detections are tiled so
+// that one CTA only sees one camera and keeps its prepared parameters in shared memory.
+//
+// HBM traffic per detection (algorithmic): read frame,x,y (24 B; +16 B of
+// pre-undistorted observation when the calibration is fixed), write r_u,r_v (16 B), the span
+// index (4 B) and the compact block row 2*P*8 B  ->  380 B/det (P=21), 524 B/det (P=30).
+// All loads/stores are unit-stride across the warp (SoA detections, column-plane Jacobian);
+// knot/coefficient/camera tables are small and stay in L2/L1.
+#pragma once
+#include "ba_ctx.cuh"
+
+namespace mvus {
+
+__global__ void cam_prep_kernel(const double* __restrict__ x, int nc, int C, int calib,
+                                const double* __restrict__ calib9, const double* __restrict__ height,
+                                double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    CamPrep c;
+    cam_prep_one(x, i, nc, C, calib != 0, calib9, height[i], c);
+    double* o = out + (size_t)i * CAMPREP_DOUBLES;
+    const double* src = reinterpret_cast<const double*>(&c);
+    for (int k = 0; k < CAMPREP_DOUBLES; ++k) o[k] = src[k];
+}
+
+// Observation with fixed calibration: K * undistortPoints(raw) once per BA instead of once
+// per evaluation (the reference recomputes it every call, common.py:126).
+__global__ void observe_kernel(const int* __restrict__ tile_cam, const int64_t* __restrict__ tile_start,
+                               const int* __restrict__ tile_cnt, const double* __restrict__ calib9,
+                               int undist, const double* __restrict__ xr, const double* __restrict__ yr,
+                               double* __restrict__ ou, double* __restrict__ ov) {
+    const int tl = blockIdx.x;
+    if ((int)threadIdx.x >= tile_cnt[tl]) return;
+    const int64_t d = tile_start[tl] + threadIdx.x;
+    const double* c = calib9 + tile_cam[tl] * 9;
+    if (undist) {
+        double xn, yn;
+        undistort5(xr[d], yr[d], c, c + 4, xn, yn);
+        ou[d] = c[0] * xn + c[2];
+        ov[d] = c[1] * yn + c[3];
+    } else {
+        ou[d] = xr[d];
+        ov[d] = yr[d];
+    }
+}
+
+struct PlaneSink {
+    double* J;
+    int64_t N, d;
+    int P;
+    __device__ __forceinline__ void put(int p, double a, double b) {
+        __stcs(J + (int64_t)p * N + d, a);
+        __stcs(J + (int64_t)(P + p) * N + d, b);
+    }
+};
+struct NullSink {
+    __device__ __forceinline__ void put(int, double, double) {}
+};
+
+__device__ __forceinline__ double block_sum_128(double v, double* sh) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) sh[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += sh[k];
+    return s;
+}
+
+// K1.  grid = tiles, block = TILE_DET.
+template <bool CALIB, bool WANTJ>
+__global__ void __launch_bounds__(TILE_DET)
+resjac_kernel(SplineView sp, const double* __restrict__ x, const double* __restrict__ camprep,
+              const int* __restrict__ tile_cam, const int64_t* __restrict__ tile_start,
+              const int* __restrict__ tile_cnt, const int64_t* __restrict__ row_off,
+              const double* __restrict__ frame, const double* __restrict__ xr,
+              const double* __restrict__ yr, const double* __restrict__ obs_u,
+              const double* __restrict__ obs_v, int undist, int opt_sync, int opt_rs, int64_t N,
+              double* __restrict__ r, int* __restrict__ span, double* __restrict__ J,
+              double* __restrict__ partial) {
+    __shared__ double s_cam[CAMPREP_DOUBLES];
+    __shared__ double s_red[TILE_DET / 32];
+    const int tl = blockIdx.x;
+    const int cam = tile_cam[tl];
+    for (int k = threadIdx.x; k < CAMPREP_DOUBLES; k += blockDim.x)
+        s_cam[k] = camprep[(size_t)cam * CAMPREP_DOUBLES + k];
+    __syncthreads();
+    const CamPrep& c = *reinterpret_cast<const CamPrep*>(s_cam);
+    const int cnt = tile_cnt[tl];
+    double sq = 0.0;
+    if ((int)threadIdx.x < cnt) {
+        const int64_t d = tile_start[tl] + threadIdx.x;
+        const double f = __ldcs(frame + d), yy = __ldcs(yr + d);
+        double xx = 0.0, ou = 0.0, ov = 0.0;
+        if (CALIB) xx = __ldcs(xr + d);
+        else { ou = __ldcs(obs_u + d); ov = __ldcs(obs_v + d); }
+        double ru, rv;
+        int sp_out;
+        FreeMask fm{opt_sync != 0, opt_rs != 0};
+        if (WANTJ) {
+            PlaneSink sink{J, N, d, 3 + (CALIB ? 15 : 6) + 12};
+            resjac_one<CALIB, true>(c, undist != 0, fm, f, xx, yy, ou, ov, sp, x, ru, rv, sp_out, sink);
+            span[d] = sp_out;
+        } else {
+            NullSink sink;
+            resjac_one<CALIB, false>(c, undist != 0, fm, f, xx, yy, ou, ov, sp, x, ru, rv, sp_out, sink);
+        }
+        const int64_t r0 = row_off[cam], ncam = (row_off[cam + 1] - r0) >> 1;
+        const int64_t local = d - (r0 >> 1);
+        __stcs(r + r0 + local, ru);
+        __stcs(r + r0 + ncam + local, rv);
+        sq = ru * ru + rv * rv;
+    }
+    const double s = block_sum_128(sq, s_red);
+    if (threadIdx.x == 0) partial[tl] = s;
+}
+
+// K1m.  grid = ceil(M / 128), block = 128.
+template <bool WANTJ>
+__global__ void __launch_bounds__(128)
+motion_kernel(SplineView sp, const double* __restrict__ x, int type, double w,
+              const double* __restrict__ tau, const int* __restrict__ tau_spl,
+              const unsigned char* __restrict__ flags, int64_t M, double* __restrict__ r_motion,
+              int* __restrict__ mbase, double* __restrict__ mJ, double* __restrict__ partial,
+              int* __restrict__ err_flag) {
+    __shared__ double s_red[4];
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double sq = 0.0;
+    if (j < M) {
+        double rr, fa[3], fc[7];
+        int base;
+        const bool ok = motion_one<WANTJ>(type, w, sp, x, tau, tau_spl, flags, j, rr, base, fa, fc);
+        if (!ok) atomicExch(err_flag, 1);
+        r_motion[j] = rr;
+        if (WANTJ) {
+            mbase[j] = base;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) mJ[(int64_t)k * M + j] = fa[k];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) mJ[(int64_t)(3 + k) * M + j] = fc[k];
+        }
+        sq = rr * rr;
+    }
+    const double s = block_sum_128(sq, s_red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// Deterministic final reduction of per-CTA partial sums (single CTA): out[0] = sum.
+__global__ void reduce_partial_kernel(const double* __restrict__ partial, int64_t n, double* __restrict__ out) {
+    __shared__ double sh[1024];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += partial[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// detections_global (common.py:105-127): time stamp and observation per detection.
+__global__ void det_global_kernel(const double* __restrict__ camprep, const int* __restrict__ tile_cam,
+                                  const int64_t* __restrict__ tile_start, const int* __restrict__ tile_cnt,
+                                  const double* __restrict__ frame, const double* __restrict__ xr,
+                                  const double* __restrict__ yr, const double* __restrict__ obs_u,
+                                  const double* __restrict__ obs_v, int calib, int undist,
+                                  double* __restrict__ t, double* __restrict__ u, double* __restrict__ v) {
+    const int tl = blockIdx.x;
+    if ((int)threadIdx.x >= tile_cnt[tl]) return;
+    const CamPrep& c = *reinterpret_cast<const CamPrep*>(camprep + (size_t)tile_cam[tl] * CAMPREP_DOUBLES);
+    const int64_t d = tile_start[tl] + threadIdx.x;
+    t[d] = c.alpha * (frame[d] + c.rho * (yr[d] * c.invH)) + c.beta;
+    if (calib) {
+        if (undist) {
+            double xn, yn;
+            undistort5(xr[d], yr[d], c.K4, c.d, xn, yn);
+            u[d] = c.K4[0] * xn + c.K4[2];
+            v[d] = c.K4[1] * yn + c.K4[3];
+        } else { u[d] = xr[d]; v[d] = yr[d]; }
+    } else { u[d] = obs_u[d]; v[d] = obs_v[d]; }
+}
+
+}  // namespace mvus

@@ -1,0 +1,103 @@
+// Multi-GPU plumbing: one process per GPU (torch.distributed launches them);
+// this library joins an NCCL communicator and sums the per-rank normal equations and costs.
+// NCCL is dlopen'ed (libnccl.so.2: the copy torch already loaded in-process, else the system
+// one) so that the library itself loads on machines without NCCL and single-GPU use never
+// touches it.
+//
+// Round-1 scheme: detections are sharded across ranks (by camera / time chunk, the caller's
+// choice), every rank accumulates its partial A, bc, D, E, W~ and they are all-reduced over
+// NVLink; the (small, exact) solve then runs redundantly on every rank, so no further
+// exchange is needed inside an LM iteration.  Per LM iteration: 1 all-reduce of the normal
+// equations + 1 of the trial cost.
+#pragma once
+#include <dlfcn.h>
+#include "ba_ctx.cuh"
+
+namespace mvus {
+
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef int (*fn_uid)(nccl_uid_t*);
+typedef int (*fn_init)(void**, int, nccl_uid_t, int);
+typedef int (*fn_destroy)(void*);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*fn_errstr)(int);
+
+struct NcclApi {
+    void* lib = nullptr;
+    fn_uid GetUniqueId = nullptr;
+    fn_init CommInitRank = nullptr;
+    fn_destroy CommDestroy = nullptr;
+    fn_allreduce AllReduce = nullptr;
+    fn_errstr GetErrorString = nullptr;
+    bool load(std::string& err) {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (lib) break;
+        }
+        if (!lib) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+        GetUniqueId = (fn_uid)dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (fn_init)dlsym(lib, "ncclCommInitRank");
+        CommDestroy = (fn_destroy)dlsym(lib, "ncclCommDestroy");
+        AllReduce = (fn_allreduce)dlsym(lib, "ncclAllReduce");
+        GetErrorString = (fn_errstr)dlsym(lib, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { err = "libnccl lacks required symbols"; return false; }
+        return true;
+    }
+};
+inline NcclApi& nccl_api() { static NcclApi a; return a; }
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;   // ncclDouble, ncclSum (stable ABI values)
+
+inline void nccl_destroy(mvus_ba_ctx* h) {
+    if (h->nccl_comm) { nccl_api().CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
+}
+
+inline int nccl_sum(mvus_ba_ctx* h, double* buf, size_t count) {
+    if (h->world <= 1 || count == 0) return MVUS_OK;
+    const int rc = nccl_api().AllReduce(buf, buf, count, NCCL_FLOAT64, NCCL_SUM, h->nccl_comm, h->st);
+    if (rc != 0) return fail(h, MVUS_ERR_NCCL, std::string("ncclAllReduce: ") +
+                             (nccl_api().GetErrorString ? nccl_api().GetErrorString(rc) : "error"));
+    return MVUS_OK;
+}
+
+inline int allreduce_normal_equations(mvus_ba_ctx* h) {
+    if (h->world <= 1) return MVUS_OK;
+    const size_t qq = (size_t)h->q * h->q;
+    int rc = nccl_sum(h, h->A.p, (size_t)h->nc * h->Pc * h->Pc + h->ncP);
+    if (!rc) rc = nccl_sum(h, h->D.p, h->nb * qq);
+    if (!rc) rc = nccl_sum(h, h->E.p, h->nb * qq);
+    if (!rc) rc = nccl_sum(h, h->W.p, (size_t)h->nb * h->q * h->ldw);
+    return rc;
+}
+
+// sum of squares lives at partial[cost_slot]; make it the global sum
+inline int allreduce_cost_slot(mvus_ba_ctx* h) {
+    return nccl_sum(h, h->partial.p + h->cost_slot, 1);
+}
+
+}  // namespace mvus
+
+extern "C" int mvus_ba_nccl_unique_id(char id_out[128]) {
+    std::string err;
+    if (!mvus::nccl_api().load(err)) return MVUS_ERR_NCCL;
+    mvus::nccl_uid_t id;
+    if (mvus::nccl_api().GetUniqueId(&id) != 0) return MVUS_ERR_NCCL;
+    memcpy(id_out, id.internal, 128);
+    return MVUS_OK;
+}
+
+extern "C" int mvus_ba_comm_init(mvus_ba_handle h, int32_t world_size, int32_t rank, const char id[128]) {
+    if (!h || !id || world_size < 1 || rank < 0 || rank >= world_size) return mvus::fail(h, MVUS_ERR_ARG, "bad argument");
+    if (world_size == 1) { h->world = 1; h->rank = 0; return MVUS_OK; }
+    std::string err;
+    if (!mvus::nccl_api().load(err)) return mvus::fail(h, MVUS_ERR_NCCL, err);
+    MV_CUDA(h, cudaSetDevice(h->desc.device));
+    mvus::nccl_uid_t uid;
+    memcpy(uid.internal, id, 128);
+    const int rc = mvus::nccl_api().CommInitRank(&h->nccl_comm, world_size, uid, rank);
+    if (rc != 0) return mvus::fail(h, MVUS_ERR_NCCL, "ncclCommInitRank failed");
+    h->world = world_size;
+    h->rank = rank;
+    return MVUS_OK;
+}

@@ -1,0 +1,758 @@
+// K2 (normal-equation accumulation) and K3 (damped solve + Levenberg-Marquardt driver).
+//
+// Replaces, for the BA of common.py:670, SciPy's TRF inner loop: LSMR on [J; sqrt(reg) I]
+// (scipy/optimize/_lsq/trf.py:488-500), the 2-D subspace trust-region solve (:508) and the
+// radius update (:526-541).  Here each LM iteration solves the damped normal equations
+//      [ A + l dA    W^T     ] [dc]   [bc]          A : camera blocks (nc x Pc x Pc, block diagonal)
+//      [ W           B + l dB] [ds] = [bs]          B : spline block, block-banded
+// EXACTLY: the spline unknowns are grouped into super-blocks of `bw` control points so that B is
+// block tridiagonal, eliminated by block cyclic reduction (log2(nb) fully parallel levels; a
+// sequential banded Cholesky would be 2e5 dependent steps at config 4), the Schur complement
+// S = A - sum_k (L_k^-1 W_k)^T (L_k^-1 W_k) is formed by an FP64 SYRK and factorised densely.
+// tests/proto/bcr_proto.py is the NumPy model of exactly this sequence.
+//
+// Why direct and not PCG: the BA normal matrix has 7 exact gauge zeros and collective
+// time-warp modes ~1e-3 against a largest eigenvalue ~1e9 (measured) -- condition
+// 1e12, far outside what CG in FP64 resolves; LM needs accurate steps along those modes.
+#pragma once
+#include "ba_ctx.cuh"
+
+namespace mvus {
+
+int evaluate(mvus_ba_ctx* h, const double* xd, bool want_j);
+
+constexpr int QMAX = 18;          // 3 * max control points per super-block (bw <= 6)
+constexpr double DIAG_MIN = 1e-6, DIAG_MAX = 1e32;
+
+// ------------------------------------------------------------------------------------------
+// K2: one CTA per tile of TILE_DET detections of one camera.  The tile's block rows
+// (2 x (P+1) values per detection: Jacobian planes + residual) are staged in shared memory;
+// thread e owns entry (a, b), a <= b, of the per-detection symmetric (P+1) x (P+1) outer
+// product and walks the tile, flushing control-point entries with one FP64 atomic per run of
+// equal span index and camera-only entries once per tile.
+// HBM traffic per detection (algorithmic): read r (16 B) + span (4 B) + J (16 P B)
+//   -> 356 B (P=21) / 500 B (P=30); writes are O(runs), not O(detections).
+template <int P>
+struct K2Cfg {
+    static constexpr int NE = (P + 1) * (P + 2) / 2;
+    static constexpr int THREADS = 256;
+    static constexpr int EPT = (NE + THREADS - 1) / THREADS;
+    static constexpr int LDT = TILE_DET + 1;
+    static constexpr size_t SMEM = (size_t)(2 * (P + 1)) * LDT * sizeof(double) + TILE_DET * sizeof(int);
+};
+
+template <int P>
+__global__ void __launch_bounds__(256)
+accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, const int* __restrict__ span,
+                  const int* __restrict__ tile_cam, const int64_t* __restrict__ tile_start,
+                  const int* __restrict__ tile_cnt, const int64_t* __restrict__ row_off, int64_t N,
+                  int Pc, int bw, int ldw, double* __restrict__ A, double* __restrict__ bc,
+                  double* __restrict__ D, double* __restrict__ E, double* __restrict__ W) {
+    using Cfg = K2Cfg<P>;
+    extern __shared__ double s_mem[];
+    double* s_J = s_mem;                                        // [2*(P+1)][LDT]
+    int* s_span = reinterpret_cast<int*>(s_mem + (size_t)2 * (P + 1) * Cfg::LDT);
+    const int tl = blockIdx.x, cam = tile_cam[tl], cnt = tile_cnt[tl];
+    const int64_t d0 = tile_start[tl];
+    const int q = 3 * bw;
+    // stage: planes 0..P-1 = u row, P = r_u, P+1..2P = v row, 2P+1 = r_v
+    for (int idx = threadIdx.x; idx < 2 * (P + 1) * TILE_DET; idx += blockDim.x) {
+        const int pl = idx / TILE_DET, t = idx - pl * TILE_DET;
+        double v = 0.0;
+        if (t < cnt) {
+            const int half = pl / (P + 1), p = pl - half * (P + 1);
+            if (p < P) v = __ldcs(J + (int64_t)(half * P + p) * N + d0 + t);
+            else {
+                const int64_t r0 = row_off[cam], ncam = (row_off[cam + 1] - r0) >> 1;
+                v = r[r0 + half * ncam + (d0 + t - (r0 >> 1))];
+            }
+        }
+        s_J[pl * Cfg::LDT + t] = v;
+    }
+    for (int t = threadIdx.x; t < TILE_DET; t += blockDim.x) s_span[t] = t < cnt ? span[d0 + t] : -1;
+    __syncthreads();
+
+    int ea[Cfg::EPT], eb[Cfg::EPT];
+    double acc[Cfg::EPT];
+#pragma unroll
+    for (int k = 0; k < Cfg::EPT; ++k) {
+        int e = threadIdx.x + k * Cfg::THREADS;
+        ea[k] = -1; eb[k] = -1; acc[k] = 0.0;
+        if (e < Cfg::NE) {
+            int a = 0;
+            while (e >= (P + 1 - a)) { e -= (P + 1 - a); ++a; }
+            ea[k] = a; eb[k] = a + e;
+        }
+    }
+    auto flush_ctrl = [&](int g) {
+#pragma unroll
+        for (int k = 0; k < Cfg::EPT; ++k) {
+            const int a = ea[k], b = eb[k];
+            if (a < 0 || a >= P || b < Pc || (b == P && a < Pc)) continue;   // not a control-point entry
+            const double v = acc[k];
+            acc[k] = 0.0;
+            if (v == 0.0) continue;
+            if (b == P) {                    // control x residual -> rhs column (b = -g)
+                const int ma = (a - Pc) / 3, ax = (a - Pc) - ma * 3;
+                const int j = g - 3 + ma;
+                if (j < 0) continue;
+                const int kb = j / bw;
+                atomicAdd(W + ((int64_t)kb * q + (j - kb * bw) * 3 + ax) * ldw + (ldw - 1), -v);
+                continue;
+            }
+            const int mb = (b - Pc) / 3, bx = (b - Pc) - mb * 3;
+            const int jb = g - 3 + mb;
+            if (jb < 0) continue;
+            const int kbb = jb / bw, lb = (jb - kbb * bw) * 3 + bx;
+            if (a < Pc) {                    // camera x control -> W
+                atomicAdd(W + ((int64_t)kbb * q + lb) * ldw + cam * Pc + a, v);
+                continue;
+            }
+            const int ma = (a - Pc) / 3, ax = (a - Pc) - ma * 3;
+            const int ja = g - 3 + ma;
+            if (ja < 0) continue;
+            const int kba = ja / bw, la = (ja - kba * bw) * 3 + ax;
+            if (kba == kbb) {
+                atomicAdd(D + ((int64_t)kba * q + la) * q + lb, v);
+                if (la != lb) atomicAdd(D + ((int64_t)kba * q + lb) * q + la, v);
+            } else {
+                atomicAdd(E + ((int64_t)kba * q + la) * q + lb, v);
+            }
+        }
+    };
+    int gprev = -1;
+    for (int t = 0; t < cnt; ++t) {
+        const int g = s_span[t];
+        if (g != gprev) {
+            if (gprev >= 0) flush_ctrl(gprev);
+            gprev = g;
+        }
+        if (g < 0) continue;
+#pragma unroll
+        for (int k = 0; k < Cfg::EPT; ++k) {
+            if (ea[k] < 0) continue;
+            const double* ja = s_J + ea[k] * Cfg::LDT + t;
+            const double* jb = s_J + eb[k] * Cfg::LDT + t;
+            acc[k] = fma(ja[0], jb[0], fma(ja[(P + 1) * Cfg::LDT], jb[(P + 1) * Cfg::LDT], acc[k]));
+        }
+    }
+    if (gprev >= 0) flush_ctrl(gprev);
+    // camera-only entries
+#pragma unroll
+    for (int k = 0; k < Cfg::EPT; ++k) {
+        const int a = ea[k], b = eb[k];
+        if (a < 0 || a >= Pc) continue;
+        if (b < Pc) {
+            const double v = acc[k];
+            if (v == 0.0) continue;
+            atomicAdd(A + ((int64_t)cam * Pc + a) * Pc + b, v);
+            if (a != b) atomicAdd(A + ((int64_t)cam * Pc + b) * Pc + a, v);
+        } else if (b == P) {
+            if (acc[k] != 0.0) atomicAdd(bc + cam * Pc + a, -acc[k]);
+        }
+    }
+}
+
+// K2m: motion rows -> spline block only.  One thread per sample.
+__global__ void accumulate_motion_kernel(const double* __restrict__ r_motion, const int* __restrict__ mbase,
+                                         const double* __restrict__ mJ, int64_t M, int bw, int ldw,
+                                         double* __restrict__ D, double* __restrict__ E,
+                                         double* __restrict__ W) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    const int base = mbase[j];
+    if (base < 0) return;
+    const int q = 3 * bw;
+    double fa[3], fc[7];
+    for (int k = 0; k < 3; ++k) fa[k] = mJ[(int64_t)k * M + j];
+    for (int k = 0; k < 7; ++k) fc[k] = mJ[(int64_t)(3 + k) * M + j];
+    const double rr = r_motion[j];
+    for (int k1 = 0; k1 < 7; ++k1) {
+        if (fc[k1] == 0.0) continue;
+        const int j1 = base + k1, kb1 = j1 / bw;
+        for (int a1 = 0; a1 < 3; ++a1) {
+            const double v1 = fc[k1] * fa[a1];
+            const int l1 = (j1 - kb1 * bw) * 3 + a1;
+            atomicAdd(W + ((int64_t)kb1 * q + l1) * ldw + (ldw - 1), -v1 * rr);
+            for (int k2 = k1; k2 < 7; ++k2) {
+                if (fc[k2] == 0.0) continue;
+                const int j2 = base + k2, kb2 = j2 / bw;
+                for (int a2 = (k2 == k1 ? a1 : 0); a2 < 3; ++a2) {
+                    const double v = v1 * fc[k2] * fa[a2];
+                    const int l2 = (j2 - kb2 * bw) * 3 + a2;
+                    if (kb1 == kb2) {
+                        atomicAdd(D + ((int64_t)kb1 * q + l1) * q + l2, v);
+                        if (l1 != l2) atomicAdd(D + ((int64_t)kb1 * q + l2) * q + l1, v);
+                    } else {
+                        atomicAdd(E + ((int64_t)kb1 * q + l1) * q + l2, v);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Marquardt diagonals (clamped) and damped working copies.
+__global__ void diag_kernel(const double* __restrict__ A, const double* __restrict__ D, int nc, int Pc,
+                            int64_t nbq, int q, int64_t n_ctrl3, double* __restrict__ diag_c,
+                            double* __restrict__ diag_s) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (int64_t)nc * Pc) {
+        const int cam = (int)(i / Pc), p = (int)(i - (int64_t)cam * Pc);
+        diag_c[i] = fmin(fmax(A[((int64_t)cam * Pc + p) * Pc + p], DIAG_MIN), DIAG_MAX);
+    }
+    if (i < nbq) {
+        const int64_t kb = i / q;
+        const int l = (int)(i - kb * q);
+        // padding unknowns (beyond the last control point) get a unit diagonal, no damping
+        diag_s[i] = i < n_ctrl3 ? fmin(fmax(D[(kb * q + l) * q + l], DIAG_MIN), DIAG_MAX) : 0.0;
+    }
+}
+
+__global__ void damp_copy_kernel(const double* __restrict__ D, const double* __restrict__ diag_s, double lam,
+                                 int64_t nbq, int q, int64_t n_ctrl3, double* __restrict__ Dw) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over nb*q*q
+    if (i >= nbq * q) return;
+    const int64_t row = i / q;
+    const int col = (int)(i - row * q);
+    double v = D[i];
+    if ((int)(row % q) == col) v = row < n_ctrl3 ? v + lam * diag_s[row] : 1.0;
+    Dw[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// One level of block cyclic reduction.  grid = blocks active at this level (indices j = i*s),
+// block = 128 threads.  sp = s/2 is the previous level's stride (0 at level 0).
+//   - apply the pending Schur updates of level-1 neighbours j -+ sp (if they were eliminated),
+//   - if j is an odd multiple of s (or the root pass): factor D_j, form ZL/ZR/W~ rows.
+// ZR is stored in E[j]; root = final pass on block 0.
+template <int Q>
+__global__ void __launch_bounds__(128)
+bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* __restrict__ Dw,
+                 double* __restrict__ Ew, double* __restrict__ Ww, double* __restrict__ ZL,
+                 int* __restrict__ fail_flag) {
+    constexpr int q = Q;
+    __shared__ double zl_m[Q * Q], zr_m[Q * Q];   // ZL, ZR of the LEFT eliminated neighbour (j - sp)
+    __shared__ double zl_p[Q * Q], zr_p[Q * Q];   // ZL, ZR of the RIGHT eliminated neighbour (j + sp)
+    __shared__ double Dj[Q * Q], El[Q * Q], Er[Q * Q];
+    __shared__ int s_bad;
+    const int64_t j = root ? 0 : (int64_t)blockIdx.x * s;
+    const bool elim = root || (((j / s) & 1) == 1);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int qq = q * q;
+    const bool has_m = sp > 0 && j - sp >= 0 && (((j - sp) / sp) & 1);
+    const bool has_p = sp > 0 && j + sp < nb && (((j + sp) / sp) & 1);
+    for (int i = tid; i < qq; i += nt) {
+        Dj[i] = Dw[j * qq + i];
+        zl_m[i] = has_m ? ZL[(j - sp) * qq + i] : 0.0;
+        zr_m[i] = has_m ? Ew[(j - sp) * qq + i] : 0.0;
+        zl_p[i] = has_p ? ZL[(j + sp) * qq + i] : 0.0;
+        zr_p[i] = has_p ? Ew[(j + sp) * qq + i] : 0.0;
+    }
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    // D_j -= ZR_m^T ZR_m + ZL_p^T ZL_p ; couplings of the eliminated block
+    for (int i = tid; i < qq; i += nt) {
+        const int a = i / q, b = i - a * q;
+        double acc = 0.0, el = 0.0, er = 0.0;
+        for (int k = 0; k < q; ++k) {
+            acc += zr_m[k * q + a] * zr_m[k * q + b] + zl_p[k * q + a] * zl_p[k * q + b];
+            el -= zr_m[k * q + a] * zl_m[k * q + b];      // rows j, cols j - s   (bridge through j - sp)
+            er -= zl_p[k * q + a] * zr_p[k * q + b];      // rows j, cols j + s   (bridge through j + sp)
+        }
+        if (sp > 0) { Dj[i] -= acc; El[i] = el; Er[i] = er; }
+    }
+    if (sp == 0 && elim && !root) {
+        // level 0: original couplings.  E[j-1] has rows j-1, cols j -> transpose; E[j] rows j, cols j+1
+        for (int i = tid; i < qq; i += nt) {
+            const int a = i / q, b = i - a * q;
+            El[i] = Ew[(j - 1) * qq + b * q + a];
+            Er[i] = (j + 1 < nb) ? Ew[j * qq + i] : 0.0;
+        }
+    }
+    __syncthreads();
+    if (elim) {
+        // Cholesky of Dj (lower, in place), q <= 18: one warp, column by column
+        if (tid < 32) {
+            for (int c = 0; c < q; ++c) {
+                double d = Dj[c * q + c];
+                if (!(d > 0.0)) { if (tid == 0) s_bad = 1; d = 1.0; }
+                d = sqrt(d);
+                __syncwarp();
+                if (tid == 0) Dj[c * q + c] = d;
+                for (int i = c + 1 + tid; i < q; i += 32) Dj[i * q + c] /= d;
+                __syncwarp();
+                for (int i = c + 1 + tid; i < q; i += 32)
+                    for (int k = c + 1; k <= i; ++k) Dj[i * q + k] -= Dj[i * q + c] * Dj[k * q + c];
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // ZL = L^-1 El, ZR = L^-1 Er : thread per column of [El | Er]
+        for (int c = tid; c < 2 * q; c += nt) {
+            double* Mx = c < q ? El : Er;
+            const int cc = c < q ? c : c - q;
+            for (int i = 0; i < q; ++i) {
+                double v = Mx[i * q + cc];
+                for (int k = 0; k < i; ++k) v -= Dj[i * q + k] * Mx[k * q + cc];
+                Mx[i * q + cc] = v / Dj[i * q + i];
+            }
+        }
+        __syncthreads();
+        if (!root)
+            for (int i = tid; i < qq; i += nt) { ZL[j * qq + i] = El[i]; Ew[j * qq + i] = Er[i]; }
+    }
+    for (int i = tid; i < qq; i += nt) Dw[j * qq + i] = Dj[i];
+    // W~ columns: pending update, then forward substitution if eliminated
+    const double* Wm = Ww + (j - sp) * (int64_t)q * ldw;
+    const double* Wp = Ww + (j + sp) * (int64_t)q * ldw;
+    double* Wj = Ww + j * (int64_t)q * ldw;
+    for (int c = tid; c < ldw; c += nt) {
+        double w[Q];
+#pragma unroll
+        for (int a = 0; a < Q; ++a) w[a] = Wj[(int64_t)a * ldw + c];
+        if (has_m)
+#pragma unroll 3
+            for (int k = 0; k < Q; ++k) {
+                const double x = Wm[(int64_t)k * ldw + c];
+#pragma unroll
+                for (int a = 0; a < Q; ++a) w[a] -= zr_m[k * Q + a] * x;
+            }
+        if (has_p)
+#pragma unroll 3
+            for (int k = 0; k < Q; ++k) {
+                const double x = Wp[(int64_t)k * ldw + c];
+#pragma unroll
+                for (int a = 0; a < Q; ++a) w[a] -= zl_p[k * Q + a] * x;
+            }
+        if (elim) {
+#pragma unroll
+            for (int i = 0; i < Q; ++i) {
+                double v = w[i];
+#pragma unroll
+                for (int k = 0; k < i; ++k) v -= Dj[i * Q + k] * w[k];
+                w[i] = v / Dj[i * Q + i];
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < Q; ++a) Wj[(int64_t)a * ldw + c] = w[a];
+    }
+    if (tid == 0 && s_bad) atomicExch(fail_flag, 1);
+}
+
+// S~ = sum over rows of W~^T W~ (lower-triangle tiles), FP64 SYRK with split-K + atomics.
+// grid = (tile pairs, K slabs), block = 16x16, 4x4 micro-tile, 64x64 output tile.
+__global__ void __launch_bounds__(256)
+syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int nt_side, int slab,
+            double* __restrict__ Sfull) {
+    __shared__ double As[16][64 + 1], Bs[16][64 + 1];
+    // decode tile pair (ti >= tj)
+    int p = blockIdx.x, ti = 0;
+    while (p >= ti + 1) { p -= ti + 1; ++ti; }
+    const int tj = p;
+    const int64_t r0 = (int64_t)blockIdx.y * slab;
+    const int64_t r1 = r0 + slab < R ? r0 + slab : R;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double acc[4][4] = {};
+    for (int64_t rr = r0; rr < r1; rr += 16) {
+        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+            const int kk = i >> 6, cc = i & 63;
+            const int64_t row = rr + kk;
+            const int ca = ti * 64 + cc, cb = tj * 64 + cc;
+            As[kk][cc] = (row < r1 && ca < ldw) ? Ww[row * ldw + ca] : 0.0;
+            Bs[kk][cc] = (row < r1 && cb < ldw) ? Ww[row * ldw + cb] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int jx = 0; jx < 4; ++jx) acc[i][jx] = fma(a[i], b[jx], acc[i][jx]);
+        }
+        __syncthreads();
+    }
+    for (int i = 0; i < 4; ++i)
+        for (int jx = 0; jx < 4; ++jx) {
+            const int row = ti * 64 + ty * 4 + i, col = tj * 64 + tx * 4 + jx;
+            if (row < ldw && col < ldw && col <= row && acc[i][jx] != 0.0)
+                atomicAdd(Sfull + (int64_t)row * ldw + col, acc[i][jx]);
+        }
+}
+
+// S = blockdiag(A) + lam * diag - S~ (lower triangle), rhs = bc - S~[ncP][:]
+__global__ void form_schur_kernel(const double* __restrict__ A, const double* __restrict__ bc,
+                                  const double* __restrict__ diag_c, double lam, int nc, int Pc, int ldw,
+                                  double* __restrict__ Sfull, double* __restrict__ rhs) {
+    const int ncP = nc * Pc;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)ncP * ncP) return;
+    const int row = (int)(i / ncP), col = (int)(i - (int64_t)row * ncP);
+    if (col > row) return;
+    double v = -Sfull[(int64_t)row * ldw + col];
+    const int cr = row / Pc, cc = col / Pc;
+    if (cr == cc) v += A[((int64_t)cr * Pc + (row - cr * Pc)) * Pc + (col - cc * Pc)];
+    if (row == col) {
+        v += lam * diag_c[row];
+        rhs[row] = bc[row] - Sfull[(int64_t)ncP * ldw + row];
+    }
+    Sfull[(int64_t)row * ldw + col] = v;
+}
+
+// Dense Cholesky + solve of the reduced camera system (n = nc*Pc <= 1152), one CTA.
+// Right-looking, lower triangle in global memory (L2 resident).  x = S^-1 rhs.
+__global__ void __launch_bounds__(1024)
+dense_chol_solve_kernel(double* __restrict__ S, int lds, int n, double* __restrict__ rhs,
+                        double* __restrict__ xout, int* __restrict__ fail_flag) {
+    __shared__ double s_col[1152];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+        double d = S[(int64_t)j * lds + j];
+        if (!(d > 0.0)) { if (tid == 0) s_bad = 1; d = 1.0; }
+        d = sqrt(d);
+        const double id = 1.0 / d;
+        for (int i = j + tid; i < n; i += nt) {
+            const double v = (i == j) ? d : S[(int64_t)i * lds + j] * id;
+            s_col[i] = v;
+            S[(int64_t)i * lds + j] = v;
+        }
+        __syncthreads();
+        // trailing update: rows i > j, cols j < k <= i ; flatten over (i,k)
+        const int mrem = n - j - 1;
+        const int64_t tot = (int64_t)mrem * (mrem + 1) / 2;
+        for (int64_t e = tid; e < tot; e += nt) {
+            // row-major lower-triangle index -> (ii, kk), ii >= kk
+            int ii = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+            while ((int64_t)(ii + 1) * (ii + 2) / 2 <= e) ++ii;
+            while ((int64_t)ii * (ii + 1) / 2 > e) --ii;
+            const int kk = (int)(e - (int64_t)ii * (ii + 1) / 2);
+            const int i = j + 1 + ii, k = j + 1 + kk;
+            S[(int64_t)i * lds + k] -= s_col[i] * s_col[k];
+        }
+        __syncthreads();
+    }
+    // forward: L y = rhs (column oriented)
+    for (int j = 0; j < n; ++j) {
+        if (tid == 0) rhs[j] = rhs[j] / S[(int64_t)j * lds + j];
+        __syncthreads();
+        const double yj = rhs[j];
+        for (int i = j + 1 + tid; i < n; i += nt) rhs[i] -= S[(int64_t)i * lds + j] * yj;
+        __syncthreads();
+    }
+    // backward: L^T x = y
+    for (int j = n - 1; j >= 0; --j) {
+        if (tid == 0) rhs[j] = rhs[j] / S[(int64_t)j * lds + j];
+        __syncthreads();
+        const double xj = rhs[j];
+        for (int i = tid; i < j; i += nt) rhs[i] -= S[(int64_t)j * lds + i] * xj;
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += nt) xout[i] = rhs[i];
+    if (tid == 0 && s_bad) atomicExch(fail_flag, 1);
+}
+
+// v[k][a] = W~[k][a][ncP] - W~[k][a][0:ncP] . dc     (one warp per row)
+__global__ void wdc_kernel(const double* __restrict__ Ww, const double* __restrict__ dc, int64_t rows, int ldw,
+                           double* __restrict__ v) {
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const double* w = Ww + row * ldw;
+    double acc = 0.0;
+    for (int c = lane; c < ldw - 1; c += 32) acc += w[c] * dc[c];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) v[row] = w[ldw - 1] - acc;
+}
+
+// Back substitution of one level: ds_k = L_k^-T ( v_k - ZL_k ds_{k-s} - ZR_k ds_{k+s} ).
+// grid = eliminated blocks of this level, block = 32.
+__global__ void bcr_back_kernel(int64_t nb, int q, int64_t s, int root, const double* __restrict__ Dw,
+                                const double* __restrict__ Ew, const double* __restrict__ ZL,
+                                double* __restrict__ ds) {
+    __shared__ double v[QMAX];
+    const int64_t k = root ? 0 : ((int64_t)blockIdx.x * 2 + 1) * s;
+    if (k >= nb) return;
+    const int qq = q * q, a = threadIdx.x;
+    if (a < q) {
+        double acc = ds[k * q + a];
+        if (!root) {
+            const double* zl = ZL + k * qq + a * q;
+            const double* dl = ds + (k - s) * q;
+            for (int b = 0; b < q; ++b) acc -= zl[b] * dl[b];
+            if (k + s < nb) {
+                const double* zr = Ew + k * qq + a * q;
+                const double* dr = ds + (k + s) * q;
+                for (int b = 0; b < q; ++b) acc -= zr[b] * dr[b];
+            }
+        }
+        v[a] = acc;
+    }
+    __syncwarp();
+    if (a == 0) {
+        const double* L = Dw + k * qq;
+        for (int i = q - 1; i >= 0; --i) {
+            double t = v[i];
+            for (int c = i + 1; c < q; ++c) t -= L[c * q + i] * v[c];
+            v[i] = t / L[i * q + i];
+        }
+    }
+    __syncwarp();
+    if (a < q) ds[k * q + a] = v[a];
+}
+
+// ------------------------------------------------------------------------------------------
+// Step bookkeeping.
+// sums[0] = sum diag*delta^2, sums[1] = b . delta, sums[2] = |delta|^2, sums[3] = |x|^2,
+// sums[4] = max |g| (as ordered-int atomicMax on the bits of a non-negative double)
+__global__ void step_dots_kernel(const double* __restrict__ dc, const double* __restrict__ ds,
+                                 const double* __restrict__ diag_c, const double* __restrict__ diag_s,
+                                 const double* __restrict__ bc, const double* __restrict__ W, int ncP,
+                                 int64_t n_ctrl3, int ldw, const double* __restrict__ x, int64_t n,
+                                 double* __restrict__ sums) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, gm = 0;
+    if (i < ncP) {
+        const double d = dc[i];
+        s0 += diag_c[i] * d * d; s1 += bc[i] * d; s2 += d * d; gm = fabs(bc[i]);
+    }
+    if (i < n_ctrl3) {
+        const double d = ds[i], b = W[i * ldw + (ldw - 1)];
+        s0 += diag_s[i] * d * d; s1 += b * d; s2 += d * d; gm = fmax(gm, fabs(b));
+    }
+    if (i < n) s3 = x[i] * x[i];
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+        gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(sums + 0, s0); atomicAdd(sums + 1, s1); atomicAdd(sums + 2, s2); atomicAdd(sums + 3, s3);
+        atomicMax(reinterpret_cast<unsigned long long*>(sums + 4), (unsigned long long)__double_as_longlong(gm));
+    }
+}
+
+// x_trial = x + delta in the reference layout; rho clamped to [0,1] under rs_bounds.
+__global__ void apply_step_kernel(const double* __restrict__ x, const double* __restrict__ dc,
+                                  const double* __restrict__ ds, int nc, int C, int Pc, int64_t n_other,
+                                  SplineView sp, int64_t n_ctrl, int rs_bounds, double* __restrict__ xt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_other) {
+        int cam, p;
+        if (i < 3 * (int64_t)nc) { p = (int)(i / nc); cam = (int)(i - (int64_t)p * nc); }
+        else { const int64_t k = i - 3 * (int64_t)nc; cam = (int)(k / C); p = 3 + (int)(k - (int64_t)cam * C); }
+        double v = x[i] + dc[cam * Pc + p];
+        if (rs_bounds && p == 2) v = fmin(fmax(v, 0.0), 1.0);
+        xt[i] = v;
+    }
+    if (i < n_ctrl) {
+        int s = 0;
+        while (s + 1 < sp.S && i >= sp.ctrl_off[s + 1]) ++s;
+        const int64_t l = i - sp.ctrl_off[s];
+        const int nco = sp.ncoef[s];
+        for (int ax = 0; ax < 3; ++ax) {
+            const int64_t xi = sp.xoff[s] + (int64_t)ax * nco + l;
+            xt[xi] = x[xi] + ds[i * 3 + ax];
+        }
+    }
+}
+
+// gradient in the reference layout: g = -b
+__global__ void gradient_kernel(const double* __restrict__ bc, const double* __restrict__ W, int nc, int C,
+                                int Pc, int64_t n_other, SplineView sp, int64_t n_ctrl, int ldw,
+                                double* __restrict__ g) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_other) {
+        int cam, p;
+        if (i < 3 * (int64_t)nc) { p = (int)(i / nc); cam = (int)(i - (int64_t)p * nc); }
+        else { const int64_t k = i - 3 * (int64_t)nc; cam = (int)(k / C); p = 3 + (int)(k - (int64_t)cam * C); }
+        g[i] = -bc[cam * Pc + p];
+    }
+    if (i < n_ctrl) {
+        int s = 0;
+        while (s + 1 < sp.S && i >= sp.ctrl_off[s + 1]) ++s;
+        const int64_t l = i - sp.ctrl_off[s];
+        const int nco = sp.ncoef[s];
+        for (int ax = 0; ax < 3; ++ax)
+            g[sp.xoff[s] + (int64_t)ax * nco + l] = -W[(i * 3 + ax) * ldw + (ldw - 1)];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host orchestration
+inline int solver_alloc(mvus_ba_ctx* h) {
+    // super-block width: reprojection rows touch 4 consecutive control points (bw >= 3);
+    // a motion row touches up to `spread` consecutive ones (bw >= spread - 1).
+    int spread = 4;
+    if (h->M > 0) {
+        std::vector<double> tau; std::vector<int> spl; std::vector<unsigned char> fl;
+        build_motion_samples(h->T, tau, spl, fl);
+        auto span_of = [&](int s, double t) {
+            const double* kn = h->T.knots.data() + h->T.knot_off[s];
+            const int k = h->T.deg[s], lmax = h->T.ncoef[s] - 1;
+            int lo = k, hi = lmax;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (kn[mid] <= t) lo = mid; else hi = mid - 1; }
+            return lo;
+        };
+        for (size_t j = 0; j < tau.size(); ++j) {
+            if (!(fl[j] & 1)) continue;
+            int lo = span_of(spl[j], tau[j]), hi = lo;
+            if (fl[j] & 2) { const int l = span_of(spl[j], tau[j - 1]); lo = std::min(lo, l); hi = std::max(hi, l); }
+            if ((fl[j] & 4) && h->desc.motion_type == MVUS_MOTION_F) {
+                const int l = span_of(spl[j], tau[j + 1]); lo = std::min(lo, l); hi = std::max(hi, l);
+            }
+            spread = std::max(spread, hi - lo + 4);
+        }
+    }
+    if (spread > 7) return fail(h, MVUS_ERR_UNSUPPORTED,
+                                "a motion-prior row touches more than 7 consecutive control points");
+    h->bw = std::max(3, spread - 1);
+    h->q = 3 * h->bw;
+    h->nb = (h->n_ctrl + h->bw - 1) / h->bw;
+    h->ncP = h->nc * h->Pc;
+    h->ldw = h->ncP + 1;
+    if (h->ncP > 1152) return fail(h, MVUS_ERR_UNSUPPORTED, "more than 1152 camera unknowns");
+    const size_t qq = (size_t)h->q * h->q;
+    MV_CUDA(h, h->A.alloc((size_t)h->nc * h->Pc * h->Pc + h->ncP));      // A then bc
+    MV_CUDA(h, h->D.alloc(h->nb * qq));
+    MV_CUDA(h, h->E.alloc(h->nb * qq));
+    MV_CUDA(h, h->W.alloc((size_t)h->nb * h->q * h->ldw));
+    MV_CUDA(h, h->Dw.alloc(h->nb * qq));
+    MV_CUDA(h, h->Ew.alloc(h->nb * qq));
+    MV_CUDA(h, h->Ww.alloc((size_t)h->nb * h->q * h->ldw));
+    MV_CUDA(h, h->ZL.alloc(h->nb * qq));
+    MV_CUDA(h, h->Sd.alloc((size_t)h->ldw * h->ldw + h->ldw));           // S~ then rhs
+    MV_CUDA(h, h->dlt_c.alloc(h->ncP));
+    MV_CUDA(h, h->dlt_s.alloc((size_t)h->nb * h->q));
+    MV_CUDA(h, h->diag_c.alloc(h->ncP));
+    MV_CUDA(h, h->diag_s.alloc((size_t)h->nb * h->q));
+    MV_CUDA(h, h->gvec.alloc(h->n));
+    MV_CUDA(h, h->xs.alloc(16));
+    return MVUS_OK;
+}
+
+// K2 + K2m at the current J / r.  Fills A, bc, D, E, W (W's last column = -g_s) and the diagonals.
+inline int accumulate(mvus_ba_ctx* h) {
+    const size_t qq = (size_t)h->q * h->q;
+    double* bc = h->A.p + (size_t)h->nc * h->Pc * h->Pc;
+    MV_CUDA(h, cudaMemsetAsync(h->A.p, 0, h->A.bytes(), h->st));
+    MV_CUDA(h, cudaMemsetAsync(h->D.p, 0, h->nb * qq * sizeof(double), h->st));
+    MV_CUDA(h, cudaMemsetAsync(h->E.p, 0, h->nb * qq * sizeof(double), h->st));
+    MV_CUDA(h, cudaMemsetAsync(h->W.p, 0, (size_t)h->nb * h->q * h->ldw * sizeof(double), h->st));
+    if (h->n_tiles > 0) {
+        if (h->P == 21) {
+            MV_CUDA(h, cudaFuncSetAttribute(accumulate_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2Cfg<21>::SMEM));
+            accumulate_kernel<21><<<h->n_tiles, 256, K2Cfg<21>::SMEM, h->st>>>(
+                h->J.p, h->r.p, h->span.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
+                h->Pc, h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
+        } else {
+            MV_CUDA(h, cudaFuncSetAttribute(accumulate_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2Cfg<30>::SMEM));
+            accumulate_kernel<30><<<h->n_tiles, 256, K2Cfg<30>::SMEM, h->st>>>(
+                h->J.p, h->r.p, h->span.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
+                h->Pc, h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
+        }
+        h->launches++;
+    }
+    if (h->M > 0) {
+        accumulate_motion_kernel<<<(int)((h->M + 127) / 128), 128, 0, h->st>>>(
+            h->r.p + 2 * h->N, h->mbase.p, h->mJ.p, h->M, h->bw, h->ldw, h->D.p, h->E.p, h->W.p);
+        h->launches++;
+    }
+    MV_CUDA(h, cudaGetLastError());
+    return MVUS_OK;
+}
+
+int allreduce_normal_equations(mvus_ba_ctx* h);   // ba_nccl.cuh
+
+inline int compute_diag(mvus_ba_ctx* h) {
+    const int64_t nbq = h->nb * h->q;
+    const int64_t cnt = std::max<int64_t>(nbq, h->ncP);
+    diag_kernel<<<(int)((cnt + 255) / 256), 256, 0, h->st>>>(h->A.p, h->D.p, h->nc, h->Pc, nbq, h->q,
+                                                            3 * h->n_ctrl, h->diag_c.p, h->diag_s.p);
+    h->launches++;
+    MV_CUDA(h, cudaGetLastError());
+    return MVUS_OK;
+}
+
+inline void launch_level(mvus_ba_ctx* h, int grid, int64_t s, int64_t sp, int root, int* fail_flag) {
+#define MV_LVL(QQ) bcr_level_kernel<QQ><<<grid, 128, 0, h->st>>>(h->nb, h->ldw, s, sp, root, h->Dw.p, h->Ew.p, h->Ww.p, h->ZL.p, fail_flag)
+    switch (h->q) {
+        case 9: MV_LVL(9); break;
+        case 12: MV_LVL(12); break;
+        case 15: MV_LVL(15); break;
+        default: MV_LVL(18); break;
+    }
+#undef MV_LVL
+    h->launches++;
+}
+
+// Solve the damped system for the current normal equations; delta -> dlt_c / dlt_s.
+// *ok = 0 if a Cholesky pivot was not positive.
+inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
+    const int q = h->q, ldw = h->ldw;
+    const int64_t nb = h->nb, nbq = nb * q;
+    const size_t qq = (size_t)q * q;
+    double* bc = h->A.p + (size_t)h->nc * h->Pc * h->Pc;
+    double* rhs = h->Sd.p + (size_t)ldw * ldw;
+    int* fail_flag = h->flag.p + 1;
+    MV_CUDA(h, cudaMemsetAsync(fail_flag, 0, sizeof(int), h->st));
+    damp_copy_kernel<<<(int)((nbq * q + 255) / 256), 256, 0, h->st>>>(h->D.p, h->diag_s.p, lam, nbq, q,
+                                                                      3 * h->n_ctrl, h->Dw.p);
+    MV_CUDA(h, cudaMemcpyAsync(h->Ew.p, h->E.p, nb * qq * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    MV_CUDA(h, cudaMemcpyAsync(h->Ww.p, h->W.p, (size_t)nbq * ldw * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+    h->launches += 1;
+    // elimination levels
+    std::vector<int64_t> levels;
+    for (int64_t s = 1; s < nb; s <<= 1) levels.push_back(s);
+    for (size_t lv = 0; lv < levels.size(); ++lv) {
+        const int64_t s = levels[lv], sp = lv ? levels[lv - 1] : 0;
+        const int64_t nact = (nb + s - 1) / s;
+        launch_level(h, (int)nact, s, sp, 0, fail_flag);
+    }
+    launch_level(h, 1, levels.empty() ? 1 : levels.back() * 2, levels.empty() ? 0 : levels.back(), 1, fail_flag);
+    // Schur complement
+    MV_CUDA(h, cudaMemsetAsync(h->Sd.p, 0, h->Sd.bytes(), h->st));
+    const int nts = (ldw + 63) / 64;
+    const int slab = 512;
+    dim3 g(nts * (nts + 1) / 2, (unsigned)((nbq + slab - 1) / slab));
+    syrk_kernel<<<g, 256, 0, h->st>>>(h->Ww.p, nbq, ldw, nts, slab, h->Sd.p);
+    form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
+        h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->Sd.p, rhs);
+    dense_chol_solve_kernel<<<1, 1024, 0, h->st>>>(h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
+    h->launches += 3;
+    // back substitution
+    wdc_kernel<<<(int)((nbq * 32 + 255) / 256), 256, 0, h->st>>>(h->Ww.p, h->dlt_c.p, nbq, ldw, h->dlt_s.p);
+    bcr_back_kernel<<<1, 32, 0, h->st>>>(nb, q, 0, 1, h->Dw.p, h->Ew.p, h->ZL.p, h->dlt_s.p);
+    h->launches += 2;
+    for (int lv = (int)levels.size() - 1; lv >= 0; --lv) {
+        const int64_t s = levels[lv];
+        const int64_t nel = (nb / s + 1) / 2;     // odd multiples of s below nb
+        if (nel <= 0) continue;
+        bcr_back_kernel<<<(int)nel, 32, 0, h->st>>>(nb, q, s, 0, h->Dw.p, h->Ew.p, h->ZL.p, h->dlt_s.p);
+        h->launches++;
+    }
+    MV_CUDA(h, cudaGetLastError());
+    int f = 0;
+    MV_CUDA(h, cudaMemcpyAsync(&f, fail_flag, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    MV_CUDA(h, cudaStreamSynchronize(h->st));
+    *ok = f ? 0 : 1;
+    return MVUS_OK;
+}
+
+inline int read_cost(mvus_ba_ctx* h, double* cost) {
+    MV_CUDA(h, cudaMemcpyAsync(h->h_pin, h->partial.p + h->cost_slot, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    MV_CUDA(h, cudaStreamSynchronize(h->st));
+    *cost = 0.5 * h->h_pin[0];
+    return MVUS_OK;
+}
+
+int allreduce_cost(mvus_ba_ctx* h, double* cost);   // ba_nccl.cuh
+
+}  // namespace mvus

@@ -1,0 +1,594 @@
+// C ABI of the B200-native mvus bundle adjustment (include/mvus_ba.h).
+// Single translation unit: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ba_ctx.cuh"
+#include "ba_kernels.cuh"
+#include "ba_solve.cuh"
+#include "ba_nccl.cuh"
+
+using namespace mvus;
+
+static std::string g_create_err;
+
+static inline double __longlong_as_double_host(double bits_as_double) {
+    // step_dots_kernel stores max|g| with an integer atomicMax on the bit pattern; the slot is
+    // read back as a double holding those same bits, so this is the identity.
+    return bits_as_double;
+}
+
+extern "C" const char* mvus_ba_version(void) { return "mvus-b200 0.1 (sm_100a, fp64)"; }
+
+extern "C" const char* mvus_ba_last_error(mvus_ba_handle h) {
+    return h ? h->err.c_str() : g_create_err.c_str();
+}
+
+extern "C" int mvus_ba_create(const mvus_ba_desc* desc, mvus_ba_handle* out) {
+    if (!desc || !out) { g_create_err = "null argument"; return MVUS_ERR_ARG; }
+    *out = nullptr;
+    if (desc->num_cams < 1) { g_create_err = "num_cams must be >= 1"; return MVUS_ERR_ARG; }
+    if (desc->motion_type < 0 || desc->motion_type > 2) { g_create_err = "bad motion_type"; return MVUS_ERR_ARG; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no usable CUDA device (there is no CPU fallback): ") +
+                       (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return MVUS_ERR_CUDA;
+    }
+    if (desc->device < 0 || desc->device >= ndev) { g_create_err = "bad device ordinal"; return MVUS_ERR_ARG; }
+    e = cudaSetDevice(desc->device);
+    if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); return MVUS_ERR_CUDA; }
+    mvus_ba_ctx* h = new mvus_ba_ctx();
+    h->desc = *desc;
+    h->nc = desc->num_cams;
+    h->C = desc->opt_calib ? 15 : 6;
+    h->Pc = 3 + h->C;
+    h->P = h->Pc + 12;
+    h->n_other = (int64_t)h->nc * h->Pc;
+    e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+        for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreate(&h->ev[k]);
+    if (e == cudaSuccess) { h->h_pin_n = 64; e = cudaMallocHost((void**)&h->h_pin, h->h_pin_n * sizeof(double)); }
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, desc->device);
+    if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); delete h; return MVUS_ERR_CUDA; }
+    *out = h;
+    return MVUS_OK;
+}
+
+extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->desc.device);
+    nccl_destroy(h);
+    cudaStreamSynchronize(h->st);
+    for (auto* b : {&h->frame, &h->xr, &h->yr, &h->obs_u, &h->obs_v, &h->calib, &h->height, &h->int_a,
+                    &h->int_b, &h->knots, &h->spanpoly, &h->span_t0, &h->lut_t0, &h->lut_invh, &h->tau,
+                    &h->x, &h->x_trial, &h->camprep, &h->r, &h->J, &h->mJ, &h->partial, &h->A, &h->D, &h->E,
+                    &h->W, &h->Dw, &h->Ew, &h->Ww, &h->ZL, &h->Sd, &h->dlt_c, &h->dlt_s, &h->diag_c,
+                    &h->diag_s, &h->gvec, &h->xs})
+        b->release();
+    for (auto* b : {&h->row_off, &h->tile_start, &h->knot_off, &h->ctrl_off, &h->xoff, &h->lut_off}) b->release();
+    for (auto* b : {&h->tile_cam, &h->tile_cnt, &h->ncoef, &h->deg, &h->lut_n, &h->lut, &h->tau_spl, &h->span,
+                    &h->mbase, &h->flag})
+        b->release();
+    h->tau_flag.release();
+    if (h->h_pin) cudaFreeHost(h->h_pin);
+    for (int k = 0; k < 8; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+// ------------------------------------------------------------------------------------------
+static int finish_dims(mvus_ba_ctx* h) {
+    if (!(h->have_det && h->have_spl)) return MVUS_OK;
+    h->n = h->n_other + 3 * h->n_ctrl;
+    h->m = 2 * h->N + h->M;
+    MV_CUDA(h, h->x.alloc(h->n));
+    MV_CUDA(h, h->x_trial.alloc(h->n));
+    MV_CUDA(h, h->camprep.alloc((size_t)h->nc * CAMPREP_DOUBLES));
+    MV_CUDA(h, h->r.alloc(h->m > 0 ? h->m : 1));
+    MV_CUDA(h, h->span.alloc(h->N > 0 ? h->N : 1));
+    MV_CUDA(h, h->partial.alloc((size_t)h->n_tiles + (h->M + 127) / 128 + 8));
+    MV_CUDA(h, h->flag.alloc(8));
+    MV_CUDA(h, cudaMemsetAsync(h->flag.p, 0, 8 * sizeof(int), h->st));
+    return MVUS_OK;
+}
+
+extern "C" int mvus_ba_set_detections(mvus_ba_handle h, const int64_t* cam_ptr, const double* frame,
+                                      const double* x, const double* y, const double* height,
+                                      const double* calib) {
+    if (!h || !cam_ptr || !height || !calib) return fail(h, MVUS_ERR_ARG, "null argument");
+    MV_CUDA(h, cudaSetDevice(h->desc.device));
+    const int nc = h->nc;
+    if (cam_ptr[0] != 0) return fail(h, MVUS_ERR_ARG, "cam_ptr[0] must be 0");
+    for (int i = 0; i < nc; ++i)
+        if (cam_ptr[i + 1] < cam_ptr[i]) return fail(h, MVUS_ERR_ARG, "cam_ptr must be non-decreasing");
+    h->cam_ptr.assign(cam_ptr, cam_ptr + nc + 1);
+    h->N = cam_ptr[nc];
+    if (h->N > 0 && (!frame || !x || !y)) return fail(h, MVUS_ERR_ARG, "null detection arrays");
+    if (h->N >= (int64_t)1 << 31) return fail(h, MVUS_ERR_UNSUPPORTED, "more than 2^31 detections per handle");
+    MV_CUDA(h, upload(h->frame, frame, (size_t)h->N, h->st));
+    MV_CUDA(h, upload(h->xr, x, (size_t)h->N, h->st));
+    MV_CUDA(h, upload(h->yr, y, (size_t)h->N, h->st));
+    MV_CUDA(h, upload(h->height, height, (size_t)nc, h->st));
+    MV_CUDA(h, upload(h->calib, calib, (size_t)nc * 9, h->st));
+    std::vector<int64_t> row_off(nc + 1);
+    for (int i = 0; i <= nc; ++i) row_off[i] = 2 * cam_ptr[i];
+    MV_CUDA(h, upload(h->row_off, row_off, h->st));
+    // tiles: TILE_DET detections of one camera each
+    std::vector<int> tcam, tcnt;
+    std::vector<int64_t> tstart;
+    for (int i = 0; i < nc; ++i)
+        for (int64_t s = cam_ptr[i]; s < cam_ptr[i + 1]; s += TILE_DET) {
+            tcam.push_back(i);
+            tstart.push_back(s);
+            tcnt.push_back((int)std::min<int64_t>(TILE_DET, cam_ptr[i + 1] - s));
+        }
+    h->n_tiles = (int)tcam.size();
+    MV_CUDA(h, upload(h->tile_cam, tcam, h->st));
+    MV_CUDA(h, upload(h->tile_start, tstart, h->st));
+    MV_CUDA(h, upload(h->tile_cnt, tcnt, h->st));
+    MV_CUDA(h, h->obs_u.alloc(h->N > 0 ? h->N : 1));
+    MV_CUDA(h, h->obs_v.alloc(h->N > 0 ? h->N : 1));
+    if (!h->desc.opt_calib && h->n_tiles > 0) {
+        observe_kernel<<<h->n_tiles, TILE_DET, 0, h->st>>>(h->tile_cam.p, h->tile_start.p, h->tile_cnt.p,
+                                                          h->calib.p, h->desc.undist_points, h->xr.p, h->yr.p,
+                                                          h->obs_u.p, h->obs_v.p);
+        MV_CUDA(h, cudaGetLastError());
+    }
+    MV_CUDA(h, cudaStreamSynchronize(h->st));
+    h->have_det = true;
+    return finish_dims(h);
+}
+
+extern "C" int mvus_ba_set_splines(mvus_ba_handle h, int32_t S, const double* interval,
+                                   const int64_t* knot_ptr, const double* knots, const int32_t* degree) {
+    if (!h || S < 1 || !interval || !knot_ptr || !knots || !degree) return fail(h, MVUS_ERR_ARG, "null argument");
+    MV_CUDA(h, cudaSetDevice(h->desc.device));
+    if (!build_spline_tables(S, interval, knot_ptr, knots, degree, h->n_other, h->T))
+        return fail(h, MVUS_ERR_ARG, "malformed spline (degree must be 1 or 3, >= degree+1 coefficients)");
+    HostSplineTables& T = h->T;
+    h->n_ctrl = T.n_ctrl;
+    MV_CUDA(h, upload(h->int_a, T.int_a, h->st));
+    MV_CUDA(h, upload(h->int_b, T.int_b, h->st));
+    MV_CUDA(h, upload(h->knots, T.knots, h->st));
+    MV_CUDA(h, upload(h->knot_off, T.knot_off, h->st));
+    MV_CUDA(h, upload(h->ncoef, T.ncoef, h->st));
+    MV_CUDA(h, upload(h->deg, T.deg, h->st));
+    MV_CUDA(h, upload(h->ctrl_off, T.ctrl_off, h->st));
+    MV_CUDA(h, upload(h->xoff, T.xoff, h->st));
+    MV_CUDA(h, upload(h->spanpoly, T.spanpoly, h->st));
+    MV_CUDA(h, upload(h->span_t0, T.span_t0, h->st));
+    MV_CUDA(h, upload(h->lut_off, T.lut_off, h->st));
+    MV_CUDA(h, upload(h->lut_n, T.lut_n, h->st));
+    MV_CUDA(h, upload(h->lut_t0, T.lut_t0, h->st));
+    MV_CUDA(h, upload(h->lut_invh, T.lut_invh, h->st));
+    MV_CUDA(h, upload(h->lut, T.lut, h->st));
+    h->sv = SplineView{S, h->int_a.p, h->int_b.p, h->knots.p, h->knot_off.p, h->ncoef.p, h->deg.p,
+                       h->ctrl_off.p, h->xoff.p, h->spanpoly.p, h->span_t0.p, h->lut_off.p, h->lut_n.p,
+                       h->lut_t0.p, h->lut_invh.p, h->lut.p};
+    h->M = 0;
+    if (h->desc.motion_type != MVUS_MOTION_NONE) {
+        std::vector<double> tau;
+        std::vector<int> spl;
+        std::vector<unsigned char> fl;
+        build_motion_samples(T, tau, spl, fl);
+        h->M = (int64_t)tau.size();
+        MV_CUDA(h, upload(h->tau, tau, h->st));
+        MV_CUDA(h, upload(h->tau_spl, spl, h->st));
+        MV_CUDA(h, upload(h->tau_flag, fl, h->st));
+    }
+    MV_CUDA(h, cudaStreamSynchronize(h->st));
+    h->have_spl = true;
+    return finish_dims(h);
+}
+
+extern "C" int mvus_ba_dims(mvus_ba_handle h, int64_t* n, int64_t* m, int64_t* N, int64_t* M, int32_t* P) {
+    if (!h) return MVUS_ERR_ARG;
+    if (!(h->have_det && h->have_spl)) return fail(h, MVUS_ERR_ARG, "set_detections and set_splines first");
+    if (n) *n = h->n;
+    if (m) *m = h->m;
+    if (N) *N = h->N;
+    if (M) *M = h->M;
+    if (P) *P = h->P;
+    return MVUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Evaluate residuals (and the Jacobian) at device vector xd.  2*cost lands in h->partial[np].
+int mvus::evaluate(mvus_ba_ctx* h, const double* xd, bool want_j) {
+    const int nc = h->nc;
+    cam_prep_kernel<<<(nc + 63) / 64, 64, 0, h->st>>>(xd, nc, h->C, h->desc.opt_calib, h->calib.p,
+                                                      h->height.p, h->camprep.p);
+    h->launches++;
+    if (want_j) {
+        MV_CUDA(h, h->J.alloc((size_t)2 * h->P * (h->N > 0 ? h->N : 1)));
+        if (h->M > 0) {
+            MV_CUDA(h, h->mJ.alloc((size_t)10 * h->M));
+            MV_CUDA(h, h->mbase.alloc((size_t)h->M));
+        }
+    }
+    if (h->n_tiles > 0) {
+#define MV_LAUNCH_K1(CAL, WJ)                                                                           \
+    resjac_kernel<CAL, WJ><<<h->n_tiles, TILE_DET, 0, h->st>>>(                                         \
+        h->sv, xd, h->camprep.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p,           \
+        h->frame.p, h->xr.p, h->yr.p, h->obs_u.p, h->obs_v.p, h->desc.undist_points, h->desc.opt_sync,  \
+        h->desc.opt_rs, h->N, h->r.p, h->span.p, h->J.p, h->partial.p)
+        if (h->desc.opt_calib) { if (want_j) MV_LAUNCH_K1(true, true); else MV_LAUNCH_K1(true, false); }
+        else { if (want_j) MV_LAUNCH_K1(false, true); else MV_LAUNCH_K1(false, false); }
+#undef MV_LAUNCH_K1
+        h->launches++;
+    }
+    int64_t np = h->n_tiles;
+    if (h->M > 0) {
+        const int gb = (int)((h->M + 127) / 128);
+        if (want_j)
+            motion_kernel<true><<<gb, 128, 0, h->st>>>(h->sv, xd, h->desc.motion_type, h->desc.motion_weight,
+                                                       h->tau.p, h->tau_spl.p, h->tau_flag.p, h->M,
+                                                       h->r.p + 2 * h->N, h->mbase.p, h->mJ.p,
+                                                       h->partial.p + np, h->flag.p);
+        else
+            motion_kernel<false><<<gb, 128, 0, h->st>>>(h->sv, xd, h->desc.motion_type, h->desc.motion_weight,
+                                                        h->tau.p, h->tau_spl.p, h->tau_flag.p, h->M,
+                                                        h->r.p + 2 * h->N, nullptr, nullptr,
+                                                        h->partial.p + np, h->flag.p);
+        np += gb;
+        h->launches++;
+    }
+    reduce_partial_kernel<<<1, 1024, 0, h->st>>>(h->partial.p, np, h->partial.p + np);
+    h->launches++;
+    h->cost_slot = np;
+    MV_CUDA(h, cudaGetLastError());
+    return MVUS_OK;
+}
+
+static int check_ready(mvus_ba_ctx* h) {
+    if (!h) return MVUS_ERR_ARG;
+    if (!(h->have_det && h->have_spl)) return fail(h, MVUS_ERR_ARG, "set_detections and set_splines first");
+    MV_CUDA(h, cudaSetDevice(h->desc.device));
+    return MVUS_OK;
+}
+
+static int check_motion_flag(mvus_ba_ctx* h) {
+    int f = 0;
+    MV_CUDA(h, cudaMemcpyAsync(&f, h->flag.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    MV_CUDA(h, cudaStreamSynchronize(h->st));
+    if (f) return fail(h, MVUS_ERR_UNSUPPORTED,
+                       "a motion-prior row touches more than 7 consecutive control points (knots denser than the unit sample grid)");
+    return MVUS_OK;
+}
+
+extern "C" int mvus_ba_residual(mvus_ba_handle h, const double* x, double* r) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!x || !r) return fail(h, MVUS_ERR_ARG, "null argument");
+    MV_CUDA(h, cudaMemcpyAsync(h->x.p, x, h->n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    rc = evaluate(h, h->x.p, false);
+    if (rc) return rc;
+    MV_CUDA(h, cudaMemcpyAsync(r, h->r.p, h->m * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    MV_CUDA(h, cudaStreamSynchronize(h->st));
+    return MVUS_OK;
+}
+
+extern "C" int mvus_ba_residual_jacobian(mvus_ba_handle h, const double* x, double* r, int32_t* span,
+                                         double* J, int32_t* mbase, double* mJ) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!x) return fail(h, MVUS_ERR_ARG, "null argument");
+    MV_CUDA(h, cudaMemcpyAsync(h->x.p, x, h->n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    rc = evaluate(h, h->x.p, true);
+    if (rc) return rc;
+    if (r) MV_CUDA(h, cudaMemcpyAsync(r, h->r.p, h->m * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (span && h->N) MV_CUDA(h, cudaMemcpyAsync(span, h->span.p, h->N * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    if (J && h->N) MV_CUDA(h, cudaMemcpyAsync(J, h->J.p, (size_t)2 * h->P * h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (mbase && h->M) MV_CUDA(h, cudaMemcpyAsync(mbase, h->mbase.p, h->M * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    if (mJ && h->M) MV_CUDA(h, cudaMemcpyAsync(mJ, h->mJ.p, (size_t)10 * h->M * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    MV_CUDA(h, cudaStreamSynchronize(h->st));
+    return check_motion_flag(h);
+}
+
+extern "C" int mvus_ba_detections_global(mvus_ba_handle h, const double* x, double* t, double* u, double* v) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!x || !t || !u || !v) return fail(h, MVUS_ERR_ARG, "null argument");
+    if (h->N == 0) return MVUS_OK;
+    MV_CUDA(h, cudaMemcpyAsync(h->x.p, x, h->n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    cam_prep_kernel<<<(h->nc + 63) / 64, 64, 0, h->st>>>(h->x.p, h->nc, h->C, h->desc.opt_calib, h->calib.p,
+                                                         h->height.p, h->camprep.p);
+    // reuse r / J storage as scratch for the three outputs
+    DevBuf<double> tmp;
+    MV_CUDA(h, tmp.alloc((size_t)3 * h->N));
+    det_global_kernel<<<h->n_tiles, TILE_DET, 0, h->st>>>(h->camprep.p, h->tile_cam.p, h->tile_start.p,
+                                                         h->tile_cnt.p, h->frame.p, h->xr.p, h->yr.p,
+                                                         h->obs_u.p, h->obs_v.p, h->desc.opt_calib,
+                                                         h->desc.undist_points, tmp.p, tmp.p + h->N, tmp.p + 2 * h->N);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t, tmp.p, h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(u, tmp.p + h->N, h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(v, tmp.p + 2 * h->N, h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    tmp.release();
+    if (e != cudaSuccess) return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e));
+    return MVUS_OK;
+}
+
+extern "C" int mvus_ba_time_resjac(mvus_ba_handle h, const double* x, int32_t reps, double* ms_mean) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!x || !ms_mean || reps < 1) return fail(h, MVUS_ERR_ARG, "bad argument");
+    MV_CUDA(h, cudaMemcpyAsync(h->x.p, x, h->n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    rc = evaluate(h, h->x.p, true);     // warm-up + allocation
+    if (rc) return rc;
+    MV_CUDA(h, cudaEventRecord(h->ev[0], h->st));
+    for (int k = 0; k < reps; ++k) {
+        rc = evaluate(h, h->x.p, true);
+        if (rc) return rc;
+    }
+    MV_CUDA(h, cudaEventRecord(h->ev[1], h->st));
+    MV_CUDA(h, cudaEventSynchronize(h->ev[1]));
+    float ms = 0.f;
+    MV_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    *ms_mean = (double)ms / reps;
+    return MVUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+static int ensure_solver(mvus_ba_ctx* h) {
+    if (h->A.p && h->W.p) return MVUS_OK;
+    return solver_alloc(h);
+}
+
+// sums[] of step_dots_kernel -> host
+static int step_scalars(mvus_ba_ctx* h, const double* xd, double out[5]) {
+    MV_CUDA(h, cudaMemsetAsync(h->xs.p, 0, 8 * sizeof(double), h->st));
+    const int64_t cnt = std::max<int64_t>(h->n, std::max<int64_t>(3 * h->n_ctrl, h->ncP));
+    double* bc = h->A.p + (size_t)h->nc * h->Pc * h->Pc;
+    step_dots_kernel<<<(int)((cnt + 255) / 256), 256, 0, h->st>>>(h->dlt_c.p, h->dlt_s.p, h->diag_c.p,
+                                                                  h->diag_s.p, bc, h->W.p, h->ncP,
+                                                                  3 * h->n_ctrl, h->ldw, xd, h->n, h->xs.p);
+    h->launches++;
+    MV_CUDA(h, cudaMemcpyAsync(h->h_pin, h->xs.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    MV_CUDA(h, cudaStreamSynchronize(h->st));
+    for (int k = 0; k < 5; ++k) out[k] = h->h_pin[k];
+    return MVUS_OK;
+}
+
+static int eval_cost(mvus_ba_ctx* h, const double* xd, bool want_j, double* cost) {
+    int rc = evaluate(h, xd, want_j);
+    if (rc) return rc;
+    rc = allreduce_cost_slot(h);
+    if (rc) return rc;
+    return read_cost(h, cost);
+}
+
+struct PhaseTimer {
+    mvus_ba_ctx* h; cudaEvent_t a, b; double* acc;
+    PhaseTimer(mvus_ba_ctx* h_, int slot, double* acc_) : h(h_), a(h_->ev[slot]), b(h_->ev[slot + 1]), acc(acc_) {
+        cudaEventRecord(a, h->st);
+    }
+    void stop() {
+        cudaEventRecord(b, h->st);
+        cudaEventSynchronize(b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        *acc += ms;
+    }
+};
+
+extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, double* r_out,
+                             mvus_ba_stats* stats) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!x0 || !x_out) return fail(h, MVUS_ERR_ARG, "null argument");
+    rc = ensure_solver(h);
+    if (rc) return rc;
+    mvus_ba_stats st;
+    memset(&st, 0, sizeof(st));
+    h->launches = 0;
+    const double ftol = h->desc.ftol, xtol = h->desc.xtol, gtol = h->desc.gtol;
+    const int max_nfev = h->desc.max_nfev > 0 ? h->desc.max_nfev : 100 * (int)std::min<int64_t>(h->n, 1000);
+    MV_CUDA(h, cudaEventRecord(h->ev[6], h->st));
+    MV_CUDA(h, cudaMemcpyAsync(h->x.p, x0, h->n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    double F = 0.0;
+    {
+        PhaseTimer t(h, 0, &st.ms_resjac);
+        rc = eval_cost(h, h->x.p, true, &F);
+        t.stop();
+        st.n_resjac++;
+    }
+    if (rc) return rc;
+    rc = check_motion_flag(h);
+    if (rc) return rc;
+    if (!std::isfinite(F)) return fail(h, MVUS_ERR_NONFINITE, "Residuals are not finite in the initial point.");
+    st.cost0 = F;
+    st.nfev = 1; st.njev = 1;
+    double lam = 1e-4, nu = 2.0;
+    int status = 0;
+    bool r_is_current = true, need_accum = true;
+    double sc[5] = {0, 0, 0, 0, 0};
+    while (st.nfev < max_nfev) {
+        if (need_accum) {
+            PhaseTimer t(h, 2, &st.ms_accum);
+            rc = accumulate(h);
+            if (!rc) rc = allreduce_normal_equations(h);
+            if (!rc) rc = compute_diag(h);
+            t.stop();
+            if (rc) return rc;
+            need_accum = false;
+        }
+        int ok = 0;
+        {
+            PhaseTimer t(h, 4, &st.ms_solve);
+            rc = solve_damped(h, lam, &ok);
+            t.stop();
+        }
+        if (rc) return rc;
+        st.lm_iterations++;
+        if (!ok) {                       // damped matrix not positive definite: more damping
+            lam *= nu; nu *= 2.0;
+            if (lam > 1e30) { status = -1; break; }
+            continue;
+        }
+        rc = step_scalars(h, h->x.p, sc);
+        if (rc) return rc;
+        st.optimality = __longlong_as_double_host(sc[4]);
+        if (st.lm_iterations == 1 || r_is_current) {
+            if (st.optimality < gtol) { status = 1; break; }
+        }
+        const double pred = 0.5 * (lam * sc[0] + sc[1]);
+        const double step_norm = std::sqrt(sc[2]), x_norm = std::sqrt(sc[3]);
+        apply_step_kernel<<<(int)((std::max<int64_t>(h->n_other, h->n_ctrl) + 255) / 256), 256, 0, h->st>>>(
+            h->x.p, h->dlt_c.p, h->dlt_s.p, h->nc, h->C, h->Pc, h->n_other, h->sv, h->n_ctrl,
+            h->desc.rs_bounds, h->x_trial.p);
+        h->launches++;
+        double Fn = 0.0;
+        {
+            PhaseTimer t(h, 0, &st.ms_trial);
+            rc = eval_cost(h, h->x_trial.p, false, &Fn);
+            t.stop();
+        }
+        if (rc) return rc;
+        st.nfev++;
+        r_is_current = false;
+        const double actual = F - Fn;
+        const double ratio = (pred > 0.0 && std::isfinite(Fn)) ? actual / pred : -1.0;
+        if (ratio > 0.0 && actual > 0.0) {
+            std::swap(h->x.p, h->x_trial.p);
+            const double t3 = 2.0 * ratio - 1.0;
+            lam *= std::max(1.0 / 3.0, 1.0 - t3 * t3 * t3);
+            lam = std::max(lam, 1e-16);
+            nu = 2.0;
+            F = Fn;
+            const bool f_small = actual < ftol * F && ratio > 0.25;
+            const bool x_small = step_norm < xtol * (xtol + x_norm);
+            if (f_small && x_small) status = 4;
+            else if (f_small) status = 2;
+            else if (x_small) status = 3;
+            if (status || st.nfev >= max_nfev) {
+                // leave r consistent with the accepted x
+                PhaseTimer t(h, 0, &st.ms_trial);
+                rc = eval_cost(h, h->x.p, false, &F);
+                t.stop();
+                r_is_current = true;
+                if (rc) return rc;
+                break;
+            }
+            {
+                PhaseTimer t(h, 0, &st.ms_resjac);
+                rc = eval_cost(h, h->x.p, true, &F);
+                t.stop();
+                st.n_resjac++;
+            }
+            if (rc) return rc;
+            st.njev++;
+            r_is_current = true;
+            need_accum = true;
+        } else {
+            lam *= nu; nu *= 2.0;
+            if (step_norm < xtol * (xtol + x_norm)) { status = 3; break; }
+            if (lam > 1e30) { status = -1; break; }
+        }
+    }
+    if (!r_is_current) {
+        PhaseTimer t(h, 0, &st.ms_trial);
+        rc = eval_cost(h, h->x.p, false, &F);
+        t.stop();
+        if (rc) return rc;
+    }
+    st.cost = F;
+    st.lambda = lam;
+    st.status = status;
+    MV_CUDA(h, cudaMemcpyAsync(x_out, h->x.p, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (r_out) MV_CUDA(h, cudaMemcpyAsync(r_out, h->r.p, h->m * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    MV_CUDA(h, cudaEventRecord(h->ev[7], h->st));
+    MV_CUDA(h, cudaEventSynchronize(h->ev[7]));
+    float ms = 0.f;
+    MV_CUDA(h, cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]));
+    st.ms_total = ms;
+    st.launches = h->launches;
+    if (stats) *stats = st;
+    return MVUS_OK;
+}
+
+extern "C" int mvus_ba_normal_equations(mvus_ba_handle h, const double* x, double* A, double* g,
+                                        double* Hss, int32_t* band_ctrl, double* Hcs, double* cost) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!x) return fail(h, MVUS_ERR_ARG, "null argument");
+    rc = ensure_solver(h);
+    if (rc) return rc;
+    MV_CUDA(h, cudaMemcpyAsync(h->x.p, x, h->n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    double F = 0.0;
+    rc = eval_cost(h, h->x.p, true, &F);
+    if (rc) return rc;
+    rc = check_motion_flag(h);
+    if (rc) return rc;
+    rc = accumulate(h);
+    if (!rc) rc = allreduce_normal_equations(h);
+    if (rc) return rc;
+    if (cost) *cost = F;
+    const int q = h->q, bw = h->bw, ldw = h->ldw, Pc = h->Pc;
+    const int64_t nb = h->nb;
+    if (A) MV_CUDA(h, cudaMemcpyAsync(A, h->A.p, (size_t)h->nc * Pc * Pc * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (g) {
+        double* bc = h->A.p + (size_t)h->nc * Pc * Pc;
+        gradient_kernel<<<(int)((std::max<int64_t>(h->n_other, h->n_ctrl) + 255) / 256), 256, 0, h->st>>>(
+            bc, h->W.p, h->nc, h->C, Pc, h->n_other, h->sv, h->n_ctrl, ldw, h->gvec.p);
+        MV_CUDA(h, cudaMemcpyAsync(g, h->gvec.p, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    }
+    MV_CUDA(h, cudaStreamSynchronize(h->st));
+    if (band_ctrl) *band_ctrl = 2 * bw;
+    if (Hss || Hcs) {
+        std::vector<double> D((size_t)nb * q * q), E((size_t)nb * q * q), W((size_t)nb * q * ldw);
+        MV_CUDA(h, cudaMemcpy(D.data(), h->D.p, D.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        MV_CUDA(h, cudaMemcpy(E.data(), h->E.p, E.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        MV_CUDA(h, cudaMemcpy(W.data(), h->W.p, W.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        const int64_t nctrl = h->n_ctrl;
+        if (Hss) {
+            const int band = 2 * bw;
+            memset(Hss, 0, (size_t)nctrl * band * 9 * sizeof(double));
+            for (int64_t i = 0; i < nctrl; ++i)
+                for (int dj = 0; dj < band && i + dj < nctrl; ++dj) {
+                    const int64_t j = i + dj, ki = i / bw, kj = j / bw;
+                    if (kj > ki + 1) continue;
+                    for (int a = 0; a < 3; ++a)
+                        for (int b = 0; b < 3; ++b) {
+                            const int la = (int)(i - ki * bw) * 3 + a, lb = (int)(j - kj * bw) * 3 + b;
+                            const double v = (ki == kj) ? D[((size_t)ki * q + la) * q + lb] : E[((size_t)ki * q + la) * q + lb];
+                            Hss[((size_t)i * band + dj) * 9 + a * 3 + b] = v;
+                        }
+                }
+        }
+        if (Hcs) {
+            const int ncP = h->ncP;
+            for (int c = 0; c < ncP; ++c)
+                for (int64_t k = 0; k < 3 * nctrl; ++k) Hcs[(size_t)c * 3 * nctrl + k] = W[(size_t)k * ldw + c];
+        }
+    }
+    return MVUS_OK;
+}
+
+extern "C" int mvus_ba_time_accumulate(mvus_ba_handle h, int32_t reps, double* ms_mean) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!ms_mean || reps < 1) return fail(h, MVUS_ERR_ARG, "bad argument");
+    if (!h->J.p) return fail(h, MVUS_ERR_ARG, "evaluate a Jacobian first (mvus_ba_time_resjac)");
+    rc = ensure_solver(h);
+    if (rc) return rc;
+    rc = accumulate(h);
+    if (rc) return rc;
+    MV_CUDA(h, cudaEventRecord(h->ev[0], h->st));
+    for (int k = 0; k < reps; ++k) {
+        rc = accumulate(h);
+        if (rc) return rc;
+    }
+    MV_CUDA(h, cudaEventRecord(h->ev[1], h->st));
+    MV_CUDA(h, cudaEventSynchronize(h->ev[1]));
+    float ms = 0.f;
+    MV_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    *ms_mean = (double)ms / reps;
+    return MVUS_OK;
+}

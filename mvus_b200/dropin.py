@@ -1,0 +1,35 @@
+"""Install the GPU bundle adjustment under the UNMODIFIED reference: replaces the methods of
+``reconstruction.common.Scene`` that sit on the BA path so that the reference's own
+``main.py`` runs with its inner loop on the B200.  See INTEGRATION.md."""
+from . import ba
+
+
+def install(common_module, satellites=True):
+    """common_module: the imported ``reconstruction.common``.  Returns the original BA."""
+    Scene = common_module.Scene
+    original = Scene.BA
+
+    def BA(self, numCam, max_iter=10, rs=False, motion_prior=False, motion_reg=False, motion_weights=1,
+           norm=False, rs_bounds=False):
+        if motion_prior:                      # discrete-trajectory mode stays on the reference
+            return original(self, numCam, max_iter=max_iter, rs=rs, motion_prior=motion_prior,
+                            motion_reg=motion_reg, motion_weights=motion_weights, norm=norm,
+                            rs_bounds=rs_bounds)
+        return ba.bundle_adjust(self, numCam, max_iter=max_iter, rs=rs, motion_reg=motion_reg,
+                                motion_weights=motion_weights, norm=norm, rs_bounds=rs_bounds)
+
+    Scene.BA = BA
+    Scene._reference_BA = original
+    if satellites:
+        orig_err, orig_rm = Scene.error_cam, Scene.remove_outliers
+
+        def error_cam(self, cam_id, mode='dist', motion_prior=False, norm=False):
+            if motion_prior or norm:
+                return orig_err(self, cam_id, mode=mode, motion_prior=motion_prior, norm=norm)
+            return ba.error_cam(self, cam_id, mode=mode)
+
+        Scene.error_cam = error_cam
+        Scene.remove_outliers = lambda self, cams, thres=30, verbose=False: ba.remove_outliers(
+            self, cams, thres=thres, verbose=verbose)
+        Scene._reference_error_cam, Scene._reference_remove_outliers = orig_err, orig_rm
+    return original

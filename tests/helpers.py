@@ -1,0 +1,103 @@
+"""Shared test helpers: compact block-row Jacobian (include/mvus_ba.h layout) -> CSR in the
+reference's (row, column) numbering, so it can be compared with the oracle's Jacobian."""
+import ctypes
+import os
+
+import numpy as np
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def expand_jacobian(fp, span, J, mbase=None, mJ=None):
+    """fp: mvus_b200.problem.FlatProblem.  Returns CSR (m x n)."""
+    N, P, nc, C, Pc = fp.N, fp.P, fp.nc, fp.C, fp.Pc
+    M = 0 if mbase is None else len(mbase)
+    m = 2 * N + M
+    J = np.asarray(J).reshape(2 * P, N)
+    cam_of = np.repeat(np.arange(nc), fp.N_cam)
+    local = np.arange(N) - fp.cam_ptr[cam_of]
+    row_u = 2 * fp.cam_ptr[cam_of] + local
+    row_v = row_u + fp.N_cam[cam_of]
+    rows, cols, vals = [], [], []
+    cov = span >= 0
+    # spline of each covered detection and local span l
+    spl = np.searchsorted(fp.ctrl_off, np.where(cov, span, 0), side='right') - 1
+    l = np.where(cov, span, 0) - fp.ctrl_off[spl]
+    for p in range(P):
+        if p == 0:
+            col = cam_of
+        elif p == 1:
+            col = nc + cam_of
+        elif p == 2:
+            col = 2 * nc + cam_of
+        elif p < Pc:
+            col = 3 * nc + cam_of * C + (p - 3)
+        else:
+            mslot, ax = divmod(p - Pc, 3)
+            j = l - 3 + mslot
+            ok = cov & (j >= 0)
+            col = fp.n_other + 3 * fp.ctrl_off[spl] + ax * fp.ncoef[spl] + j
+            for rr, plane in ((row_u, J[p]), (row_v, J[P + p])):
+                rows.append(rr[ok]); cols.append(col[ok]); vals.append(plane[ok])
+            continue
+        for rr, plane in ((row_u, J[p]), (row_v, J[P + p])):
+            rows.append(rr[cov]); cols.append(col[cov]); vals.append(plane[cov])
+    if M:
+        mJ = np.asarray(mJ).reshape(10, M)
+        act = np.nonzero(mbase >= 0)[0]
+        b = mbase[act]
+        spl = np.searchsorted(fp.ctrl_off, b, side='right') - 1
+        for k in range(7):
+            j = b + k - fp.ctrl_off[spl]
+            ok = j < fp.ncoef[spl]
+            for ax in range(3):
+                col = fp.n_other + 3 * fp.ctrl_off[spl] + ax * fp.ncoef[spl] + j
+                rows.append(2 * N + act[ok]); cols.append(col[ok]); vals.append((mJ[ax, act] * mJ[3 + k, act])[ok])
+    rows = np.concatenate(rows); cols = np.concatenate(cols); vals = np.concatenate(vals)
+    A = sp.coo_matrix((vals, (rows, cols)), shape=(m, fp.n)).tocsr()
+    A.sum_duplicates()
+    return A
+
+
+def build_emul():
+    """Build tests/emul/libmvus_emul.so (host compile of the kernels' math) if needed."""
+    import subprocess
+    d = os.path.join(ROOT, 'tests', 'emul')
+    so = os.path.join(d, 'libmvus_emul.so')
+    srcs = [os.path.join(d, 'emul.cpp'), os.path.join(ROOT, 'mvus_b200', 'csrc', 'ba_math.cuh'),
+            os.path.join(ROOT, 'mvus_b200', 'csrc', 'ba_tables.hpp')]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(['g++', '-O2', '-shared', '-fPIC', '-Wno-unknown-pragmas', '-o', so, srcs[0]])
+    return ctypes.CDLL(so)
+
+
+def emul_resjac(fp, x):
+    """Run the host emulation of K1/K1m on FlatProblem fp at x -> (r, span, J, mbase, mJ)."""
+    lib = build_emul()
+    dp = ctypes.POINTER(ctypes.c_double)
+    ip = ctypes.POINTER(ctypes.c_int32)
+    lp = ctypes.POINTER(ctypes.c_int64)
+
+    def D(a):
+        return a.ctypes.data_as(dp)
+    lib.emul_motion_count.restype = ctypes.c_int64
+    interval = np.ascontiguousarray(fp.interval.reshape(-1))
+    M = 0
+    if fp.motion_type:
+        M = lib.emul_motion_count(fp.S, D(interval), fp.knot_ptr.ctypes.data_as(lp), D(fp.knots),
+                                  fp.degree.ctypes.data_as(ip))
+    r = np.zeros(2 * fp.N + M)
+    span = np.zeros(fp.N, dtype=np.int32)
+    J = np.zeros(2 * fp.P * fp.N)
+    mbase = np.zeros(M, dtype=np.int32)
+    mJ = np.zeros(10 * M)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    rc = lib.emul_resjac(fp.nc, int(fp.opt_calib), int(fp.undist), int(fp.opt_sync), int(fp.opt_rs),
+                         fp.motion_type, ctypes.c_double(fp.motion_weight), fp.cam_ptr.ctypes.data_as(lp),
+                         D(fp.frame), D(fp.x_raw), D(fp.y_raw), D(fp.height), D(fp.calib), fp.S,
+                         D(interval), fp.knot_ptr.ctypes.data_as(lp), D(fp.knots),
+                         fp.degree.ctypes.data_as(ip), D(x), D(r), span.ctypes.data_as(ip), D(J),
+                         mbase.ctypes.data_as(ip), D(mJ))
+    assert rc == 0, rc
+    return r, span, J, mbase, mJ
