@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""Benchmark of the mvus BA hot path (contract: see the task statement / DESIGN.md section 7).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--cams C --det D --coef NCOEF] [--no-cpu-baseline]
+
+A step = one Levenberg-Marquardt iteration of the bundle adjustment (linear solve(s) for the
+damped step, trial residual evaluation, and -- when the step is accepted -- residual+Jacobian
+and normal-equation accumulation at the new point) on the synthetic flight named in
+config.workload.  value = detections x LM iterations per second over all GPUs, inputs resident
+in HBM, device-timed with CUDA events inside the library; e2e = the same through Scene.BA with
+host buffers (H2D of the detections and D2H of the result inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'BA LM throughput (detections x LM iterations / s; resid+Jacobian Mdet/s and LM iters/s alongside)'
+UNIT = 'Mdet/s'
+BA_KW = dict(rs=True, motion_reg=True, motion_weights=1e4)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cams', type=int, default=64)
+    ap.add_argument('--det', type=int, default=1000000, help='detections per camera')
+    ap.add_argument('--coef', type=int, default=200000, help='spline coefficients per axis')
+    ap.add_argument('--sample-cams', type=int, default=4)
+    ap.add_argument('--sample-det', type=int, default=1500)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def make_workload(cams, det, coef):
+    from concurrent.futures import ThreadPoolExecutor
+    from mvus_b200 import synth
+    # simulate cameras in parallel threads (NumPy releases the GIL in the heavy ufuncs)
+    orig = synth.simulate_detections
+    pool = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
+    futures = []
+
+    def deferred(*a, **k):
+        # each camera needs its own generator state to be reproducible under threading
+        a = list(a)
+        a[6] = np.random.default_rng(1000 + len(futures))
+        fut = pool.submit(orig, *a, **k)
+        futures.append(fut)
+        return fut
+    synth.simulate_detections = deferred
+    try:
+        fl, truth = synth.make_flight(nc=cams, det_per_cam=det, n_coef=coef, rolling_shutter=True,
+                                      distortion=True, motion_type='F', motion_weights=1e4, uncovered=0.0)
+    finally:
+        synth.simulate_detections = orig
+    fl.detections = [f.result() for f in fl.detections]
+    pool.shutdown()
+    return fl
+
+
+def workload_name(a):
+    return ('synthetic %d-camera x %d-detection flight, %d spline coefficients/axis, rolling shutter + '
+            'motion F (w=1e4), fixed calibration' % (a.cams, a.det, a.coef))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k] == 'Active' for r in self.rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def cpu_reference_run(a, steps, warmup):
+    """The reference's CPU path on a bounded sample of the workload: oracle port of
+    Scene.BA's least_squares call (2-point FD on the jac_BA pattern, TRF+LSMR), all host threads
+    BLAS wants.  Returns (Mdet/s, dict)."""
+    from mvus_b200 import synth
+    from oracle import ba_oracle
+    fl, _ = synth.make_flight(nc=a.sample_cams, det_per_cam=a.sample_det, rolling_shutter=True,
+                              distortion=True, motion_type='F', motion_weights=1e4, uncovered=0.0)
+    prob = ba_oracle.Problem(fl, fl.numCam, **BA_KW)
+    N = int(sum(prob.N))
+    t0 = time.perf_counter()
+    A = prob.pattern_near3(prob.x0)
+    t_pat = time.perf_counter() - t0
+    if warmup:
+        prob.shipped_solve(prob.x0, max_nfev=2, pattern=A)
+    t0 = time.perf_counter()
+    res = prob.shipped_solve(prob.x0, max_nfev=steps + 1, pattern=A)
+    dt = time.perf_counter() - t0
+    iters = max(res.nfev - 1, 1)
+    val = N * iters / dt / 1e6
+    info = {'value': val, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+            'sample': '%d cameras x %d detections (N=%d, n=%d, m=%d), same settings; %d LM iterations in %.2f s '
+                      '(%.3f LM it/s; jac_BA pattern %.2f s not included)' % (
+                          a.sample_cams, a.sample_det, N, prob.n, prob.m, iters, dt, iters / dt, t_pat),
+            'lm_iters_per_s': iters / dt, 'final_cost': float(res.cost)}
+    return val, info, dt, iters
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    cfg = {'workload': workload_name(a), 'cams': a.cams, 'det_per_cam': a.det, 'coef_per_axis': a.coef,
+           'l2_policy': 'inputs (J planes >= 0.3 GB) exceed L2; no flush needed',
+           'parallelism': 'detections sharded by camera+time chunk over %d GPU(s), NCCL all-reduce of normal equations' % world}
+
+    if a.impl == 'reference':
+        if rank != 0:
+            return
+        val, info, dt, iters = cpu_reference_run(a, a.steps, a.warmup)
+        cfg['sample'] = info['sample']
+        line = {'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': iters, 'warmup': a.warmup,
+                'ms_per_step': dt / iters * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+                'dtype': 'f64', 'data': 'synthetic', 'config': cfg, 'impl': 'reference', 'cpu_baseline': info,
+                'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'gpu_launches': 0, 'lm_iters_per_s': info['lm_iters_per_s']}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mvus_b200 import _cabi, ba, shard
+    from mvus_b200.problem import FlatProblem
+    torch.cuda.set_device(local)
+    ba.DEVICE = local
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        shard.init_comm()
+
+    t0 = time.perf_counter()
+    fl = make_workload(a.cams, a.det, a.coef)
+    t_gen = time.perf_counter() - t0
+    N_total = int(sum(d.shape[1] for d in fl.detections))
+    if world > 1:
+        fl = shard.shard_scene(fl, rank, world)
+    fp = FlatProblem(fl, fl.numCam, **BA_KW)
+
+    # ---- device-resident timing -----------------------------------------------------------
+    hd = _cabi.Handle(fp, device=local, ftol=0.0, xtol=0.0, gtol=0.0, max_nfev=a.warmup + 1)
+    if world > 1:
+        hd.comm_init(*ba._COMM)
+    hd.solve(fp.x0, want_r=False)                                   # warm-up steps
+    ms_k1 = hd.time_resjac(fp.x0, reps=3)                           # K1+K1m alone (roofline)
+    ms_k2 = hd.time_accumulate(reps=3)                              # K2+K2m alone
+    hd.lib.mvus_ba_destroy(hd.h)
+    hd.h = None
+    hd = _cabi.Handle(fp, device=local, ftol=0.0, xtol=0.0, gtol=0.0, max_nfev=a.steps + 1)
+    if world > 1:
+        hd.comm_init(*ba._COMM)
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    x, _, st = hd.solve(fp.x0, want_r=False)
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    steps_done = st.nfev - 1
+    ms = torch.tensor([st.ms_total, ms_k1, ms_k2, st.ms_resjac, st.ms_accum, st.ms_solve, st.ms_trial],
+                      dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.cpu().tolist()
+    hd.close()
+    value = N_total * steps_done / (ms[0] / 1e3) / 1e6
+
+    # ---- end to end through the public API (host buffers) -----------------------------------
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    res = fl.BA(fl.numCam, max_iter=a.steps + 1, ftol=0.0, xtol=0.0, gtol=0.0, **BA_KW) \
+        if False else ba.bundle_adjust(fl, fl.numCam, max_iter=a.steps + 1, ftol=0.0, xtol=0.0, gtol=0.0, **BA_KW)
+    torch.cuda.synchronize()
+    dt_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(dt_e2e, op=dist.ReduceOp.MAX)
+    dt_e2e = float(dt_e2e.item())
+    e2e_steps = max(res.nfev - 1, 1)
+    e2e_val = N_total * e2e_steps / dt_e2e / 1e6
+    h2d = (3 * fp.N * 8 + fp.n * 8) / e2e_steps
+    d2h = (fp.n * 8 + (2 * fp.N + hd.M) * 8 + 2 * 3 * fp.N * 8) / e2e_steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
+    P = fp.P
+    N_loc = fp.N
+    k1_bytes = N_loc * (24 + 16 + 4 + 16 * P)            # 380 B/det (P=21)
+    k2_bytes = N_loc * (16 + 4 + 16 * P)                 # 356 B/det
+    phases = {'resjac_K1': {'ms': ms[1], 'algorithmic_GBps': k1_bytes / ms[1] / 1e6, 'bytes_per_det': 44 + 16 * P},
+              'accumulate_K2': {'ms': ms[2], 'algorithmic_GBps': k2_bytes / ms[2] / 1e6, 'bytes_per_det': 20 + 16 * P},
+              'solve_share_ms': ms[5], 'resjac_share_ms': ms[3], 'accum_share_ms': ms[4], 'trial_share_ms': ms[6]}
+    dom = 'resjac_K1' if ms[3] >= ms[4] else 'accumulate_K2'
+    ach = phases[dom]['algorithmic_GBps']
+    roof = {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+            'traffic': None, 'peak_source': peak_src,
+            'note': 'per-rank detections x %d B/det / CUDA-event time of the kernel run alone (3 reps)' % phases[dom]['bytes_per_det']}
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps_done, 'warmup': a.warmup,
+            'ms_per_step': ms[0] / max(steps_done, 1), 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+            'lm_iters_per_s': steps_done / (ms[0] / 1e3),
+            'resid_jac_mdet_per_s': N_total / (ms[1] / 1e3) / 1e6,
+            'roofline': roof, 'phases': phases, 'clocks': clocks,
+            'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'seconds': dt_e2e, 'steps': e2e_steps},
+            'gpu_launches': int(st.launches), 'final_cost': st.cost, 'cost0': st.cost0,
+            'workload_gen_s': t_gen}
+    if world == 1 and not a.no_cpu_baseline:
+        _, info, _, _ = cpu_reference_run(a, 9, 1)
+        line['cpu_baseline'] = info
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

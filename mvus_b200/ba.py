@@ -198,33 +198,52 @@ def _all_detect_to_traj(scene, cams):
 
 def bundle_adjust(scene, numCam, max_iter=10, rs=False, motion_prior=False, motion_reg=False,
                   motion_weights=1, norm=False, rs_bounds=False, ftol=1e-8, xtol=1e-12, gtol=1e-8,
-                  return_handle=False):
+                  return_handle=False, bookkeeping=True):
     """Scene.BA(numCam, max_iter, rs, motion_prior, motion_reg, motion_weights, norm, rs_bounds)
     -- reference signature (common.py:441); ``max_iter`` is scipy's max_nfev (common.py:670),
     xtol = 1e-12 as the reference passes, ftol / gtol = scipy defaults."""
     if motion_prior:
         raise NotImplementedError('BA(motion_prior=True) (discrete-trajectory mode, common.py:466-467) is '
                                   'never used by main.py and is not implemented; see SURVEY.md 8b')
+    assert len(scene.alpha) == scene.numCam and len(scene.beta) == scene.numCam, \
+        'The Number of alpha and beta is wrong'
     fp = FlatProblem(scene, numCam, rs=rs, motion_reg=motion_reg, motion_weights=motion_weights,
                      rs_bounds=rs_bounds, max_iter=max_iter)
     print('Number of BA parameters is {}'.format(fp.n))
+    interval = np.asarray(scene.spline['int'], dtype=np.float64)
+    others = [i for i in range(scene.numCam) if i not in fp.seq]
 
-    # visibility with PRE-BA parameters (common.py:493)
-    compute_visibility(scene)
+    def refresh(hd, x, with_visible):
+        """detections_global (and visible) of the optimised cameras from the BA handle itself
+        (one upload of the detections serves visibility, solve and refresh); cameras outside
+        sequence[:numCam] go through a second, small handle."""
+        t, u, v = hd.detections_global(x)
+        dg = list(scene.detections_global) if len(scene.detections_global) == scene.numCam \
+            else [[] for _ in range(scene.numCam)]
+        for k, i in enumerate(fp.seq):
+            a, b = fp.cam_ptr[k], fp.cam_ptr[k + 1]
+            dg[i] = np.vstack((t[a:b], u[a:b], v[a:b]))
+        scene.detections_global = dg
+        if others:
+            detection_to_global(scene, others)
+        if with_visible:
+            scene.visible = [_interval_membership(scene.detections_global[i][0], interval)
+                             for i in range(scene.numCam)]
 
     print('Doing BA with {} cameras...\n'.format(numCam))
     hd = _cabi.Handle(fp, device=DEVICE, ftol=ftol, xtol=xtol, gtol=gtol)
     try:
         if _COMM is not None and _COMM[0] > 1:
             hd.comm_init(*_COMM)
+        refresh(hd, fp.x0, True)            # visibility with PRE-BA parameters (common.py:493)
         x, r, st = hd.solve(fp.x0)
+        fp.unpack_into(scene, x)            # common.py:672-692
+        refresh(hd, x, False)               # common.py:695
     finally:
         if not return_handle:
             hd.close()
 
-    fp.unpack_into(scene, x)
-    detection_to_global(scene)
-    if motion_reg:
+    if motion_reg and bookkeeping:
         spline_to_traj(scene)                      # common.py:379 leaves traj = unit-step samples
         unit_traj = scene.traj
         _all_detect_to_traj(scene, fp.seq)

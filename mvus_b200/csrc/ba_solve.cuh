@@ -22,7 +22,7 @@ namespace mvus {
 int evaluate(mvus_ba_ctx* h, const double* xd, bool want_j);
 
 constexpr int QMAX = 18;          // 3 * max control points per super-block (bw <= 6)
-constexpr double DIAG_MIN = 1e-6, DIAG_MAX = 1e32;
+constexpr double DIAG_MIN = 1e-6, DIAG_MAX = 1e32, DIAG_FLOOR_FRAC = 1e-2;
 
 // ------------------------------------------------------------------------------------------
 // K2: one CTA per tile of TILE_DET detections of one camera.  The tile's block rows
@@ -218,6 +218,21 @@ __global__ void damp_copy_kernel(const double* __restrict__ D, const double* __r
     double v = D[i];
     if ((int)(row % q) == col) v = row < n_ctrl3 ? v + lam * diag_s[row] : 1.0;
     Dw[i] = v;
+}
+
+// Floor on the control-point scaling: d_i = max(d_i, frac * mean(d)).  Control points all carry
+// the same unit (metres); ones with almost no data (ends of an interval) would otherwise get
+// almost no damping and jump by metres in one step while the quartic KE prior explodes
+// (measured on the 'covered' test flight).
+__global__ void sum_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double s = i < n ? v[i] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(out, s);
+}
+__global__ void floor_kernel(double* __restrict__ v, int64_t n, const double* __restrict__ sum, double frac) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = fmax(v[i], frac * sum[0] / (double)n);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -677,6 +692,13 @@ inline int compute_diag(mvus_ba_ctx* h) {
     diag_kernel<<<(int)((cnt + 255) / 256), 256, 0, h->st>>>(h->A.p, h->D.p, h->nc, h->Pc, nbq, h->q,
                                                             3 * h->n_ctrl, h->diag_c.p, h->diag_s.p);
     h->launches++;
+    const int64_t n3 = 3 * h->n_ctrl;
+    if (n3 > 0) {
+        MV_CUDA(h, cudaMemsetAsync(h->xs.p + 8, 0, sizeof(double), h->st));
+        sum_kernel<<<(int)((n3 + 255) / 256), 256, 0, h->st>>>(h->diag_s.p, n3, h->xs.p + 8);
+        floor_kernel<<<(int)((n3 + 255) / 256), 256, 0, h->st>>>(h->diag_s.p, n3, h->xs.p + 8, DIAG_FLOOR_FRAC);
+        h->launches += 2;
+    }
     MV_CUDA(h, cudaGetLastError());
     return MVUS_OK;
 }

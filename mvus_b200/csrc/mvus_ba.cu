@@ -405,11 +405,26 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
     if (!std::isfinite(F)) return fail(h, MVUS_ERR_NONFINITE, "Residuals are not finite in the initial point.");
     st.cost0 = F;
     st.nfev = 1; st.njev = 1;
-    double lam = 1e-4, nu = 2.0;
+    // Levenberg-Marquardt with trust-region control of the step length (More, as in MINPACK's
+    // lmpar, and the radius update of scipy/optimize/_lsq/trf.py:526-541): lambda is chosen so
+    // that the scaled step norm |delta|_D is within 25% of the radius Delta; a poor step shrinks
+    // Delta to |delta|_D / 4, a very good one at the boundary doubles it.  Re-solving for a new
+    // lambda costs linear solves but no residual evaluations (nfev is what max_iter caps).
+    const double lam_min = 1e-10;
+    double lam = 1e-4, Delta = -1.0;
     int status = 0;
     bool r_is_current = true, need_accum = true;
     double sc[5] = {0, 0, 0, 0, 0};
-    while (st.nfev < max_nfev) {
+    auto solve_norm = [&](double l, int* ok, double* nrm) -> int {
+        PhaseTimer t(h, 4, &st.ms_solve);
+        int e = solve_damped(h, l, ok);
+        if (!e && *ok) e = step_scalars(h, h->x.p, sc);
+        t.stop();
+        st.lm_iterations++;
+        *nrm = *ok ? std::sqrt(sc[0]) : 1e300;
+        return e;
+    };
+    while (st.nfev < max_nfev && status == 0) {
         if (need_accum) {
             PhaseTimer t(h, 2, &st.ms_accum);
             rc = accumulate(h);
@@ -420,24 +435,38 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
             need_accum = false;
         }
         int ok = 0;
-        {
-            PhaseTimer t(h, 4, &st.ms_solve);
-            rc = solve_damped(h, lam, &ok);
-            t.stop();
-        }
+        double nrm = 0.0;
+        rc = solve_norm(lam, &ok, &nrm);
         if (rc) return rc;
-        st.lm_iterations++;
-        if (!ok) {                       // damped matrix not positive definite: more damping
-            lam *= nu; nu *= 2.0;
-            if (lam > 1e30) { status = -1; break; }
-            continue;
+        if (ok && Delta < 0.0) Delta = nrm;
+        // bracket / secant search on lambda (log scale) for |delta|_D ~ Delta
+        double lo_l = -1, lo_n = 0, hi_l = -1, hi_n = 0;
+        for (int its = 0; its < 10; ++its) {
+            if (!ok || nrm > 1.25 * Delta) { lo_l = lam; lo_n = nrm; }
+            else if (nrm < 0.75 * Delta && lam > lam_min) { hi_l = lam; hi_n = nrm; }
+            else break;
+            if (lo_l > 0 && hi_l > 0 && lo_n < 1e299) {
+                const double a = std::log(lo_l), b = std::log(hi_l);
+                const double fa = 1.0 / lo_n - 1.0 / Delta, fb = 1.0 / hi_n - 1.0 / Delta;
+                double t = a - fa * (b - a) / (fb - fa);
+                t = std::min(std::max(t, a + 0.1 * (b - a)), b - 0.1 * (b - a));
+                lam = std::exp(t);
+            } else if (lo_l > 0 && hi_l > 0) {
+                lam = std::sqrt(lo_l * hi_l);
+            } else if (lo_l > 0) {
+                const double f = ok ? std::pow(std::max(nrm / Delta, 2.0), 1.5) : 10.0;
+                lam = std::max(lam * f, lam * 4.0);
+                if (lam > 1e30) break;
+            } else {
+                lam = std::max(lam * std::pow(std::min(nrm / Delta, 0.5), 1.5), lam_min);
+            }
+            rc = solve_norm(lam, &ok, &nrm);
+            if (rc) return rc;
+            if (ok && Delta < 0.0) Delta = nrm;
         }
-        rc = step_scalars(h, h->x.p, sc);
-        if (rc) return rc;
+        if (!ok) { status = -1; break; }
         st.optimality = __longlong_as_double_host(sc[4]);
-        if (st.lm_iterations == 1 || r_is_current) {
-            if (st.optimality < gtol) { status = 1; break; }
-        }
+        if (r_is_current && st.optimality < gtol) { status = 1; break; }
         const double pred = 0.5 * (lam * sc[0] + sc[1]);
         const double step_norm = std::sqrt(sc[2]), x_norm = std::sqrt(sc[3]);
         apply_step_kernel<<<(int)((std::max<int64_t>(h->n_other, h->n_ctrl) + 255) / 256), 256, 0, h->st>>>(
@@ -455,21 +484,19 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
         r_is_current = false;
         const double actual = F - Fn;
         const double ratio = (pred > 0.0 && std::isfinite(Fn)) ? actual / pred : -1.0;
-        if (ratio > 0.0 && actual > 0.0) {
+        if (ratio < 0.25) Delta = 0.25 * nrm;
+        else if (ratio > 0.75 && nrm > 0.7 * Delta) Delta *= 2.0;
+        const bool x_small = step_norm < xtol * (xtol + x_norm);
+        if (std::isfinite(Fn) && actual > 0.0) {
             std::swap(h->x.p, h->x_trial.p);
-            const double t3 = 2.0 * ratio - 1.0;
-            lam *= std::max(1.0 / 3.0, 1.0 - t3 * t3 * t3);
-            lam = std::max(lam, 1e-16);
-            nu = 2.0;
+            if (ratio > 0.75) lam = std::max(lam / 3.0, lam_min);
+            const bool f_small = actual < ftol * Fn && ratio > 0.25;
             F = Fn;
-            const bool f_small = actual < ftol * F && ratio > 0.25;
-            const bool x_small = step_norm < xtol * (xtol + x_norm);
             if (f_small && x_small) status = 4;
             else if (f_small) status = 2;
             else if (x_small) status = 3;
             if (status || st.nfev >= max_nfev) {
-                // leave r consistent with the accepted x
-                PhaseTimer t(h, 0, &st.ms_trial);
+                PhaseTimer t(h, 0, &st.ms_trial);      // leave r consistent with the accepted x
                 rc = eval_cost(h, h->x.p, false, &F);
                 t.stop();
                 r_is_current = true;
@@ -486,10 +513,8 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
             st.njev++;
             r_is_current = true;
             need_accum = true;
-        } else {
-            lam *= nu; nu *= 2.0;
-            if (step_norm < xtol * (xtol + x_norm)) { status = 3; break; }
-            if (lam > 1e30) { status = -1; break; }
+        } else if (x_small) {
+            status = 3;
         }
     }
     if (!r_is_current) {

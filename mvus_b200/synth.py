@@ -29,8 +29,13 @@ README_DIST = np.array([-0.260720634999793, 0.07494782427852716, -0.000136314628
 
 def gt_trajectory(tau, fps_ref=30.0, deriv=False):
     """Ground-truth 3D position (3xn, metres) at global time ``tau`` (reference-camera
-    frames).  Bounded helix-like curve, smooth at the scale of a knot span."""
+    frames).  Bounded helix-like curve, smooth at the scale of a knot span.  ``deriv=True``
+    returns d2X/dtau2 instead."""
     s = np.asarray(tau, dtype=np.float64) / fps_ref
+    if deriv:
+        return np.vstack((-1.25 * np.cos(0.5 * s) - 0.0169 * np.sin(0.13 * s),
+                          -1.25 * np.sin(0.5 * s) - 0.0289 * np.cos(0.17 * s),
+                          -0.08 * np.sin(0.2 * s) - 0.000961 * np.sin(0.031 * s))) / fps_ref ** 2
     X = np.vstack((5.0 * np.cos(0.5 * s) + 1.0 * np.sin(0.13 * s),
                    5.0 * np.sin(0.5 * s) + 1.0 * np.cos(0.17 * s),
                    3.0 + 2.0 * np.sin(0.2 * s) + 1.0 * np.sin(0.031 * s)))
@@ -94,6 +99,14 @@ def fit_spline(t0, t1, n_coef, fps_ref=30.0):
     n_coef = max(int(n_coef), 4)
     interior = np.linspace(t0, t1, n_coef - 2)[1:-1]
     knots = np.concatenate((np.full(4, t0), interior, np.full(4, t1)))
+    if n_coef > 1500:
+        # O(n) quasi-interpolant (exact for quadratics): c_j = f(xi_j) + mu_j/2 f''(xi_j) with the
+        # Greville abscissa xi_j and mu_j = blossom(t^2) - xi_j^2; make_lsq_spline is O(n^2).
+        a, b, c3 = knots[1:n_coef + 1], knots[2:n_coef + 2], knots[3:n_coef + 3]
+        xi = (a + b + c3) / 3.0
+        mu = (a * b + a * c3 + b * c3) / 3.0 - xi * xi
+        c = gt_trajectory(xi, fps_ref) + 0.5 * mu * gt_trajectory(xi, fps_ref, deriv=True)
+        return [knots, [c[0].copy(), c[1].copy(), c[2].copy()], 3]
     ns = max(4 * n_coef, 64)
     ts = np.linspace(t0, t1, ns)
     spl = make_lsq_spline(ts, gt_trajectory(ts, fps_ref).T, knots, k=3)

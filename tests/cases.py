@@ -17,6 +17,12 @@ CASES = {
     # everything strictly covered, low noise: well-posed optimum for the cost-parity test
     'covered': (dict(nc=4, det_per_cam=400, rolling_shutter=True, distortion=True, uncovered=-0.05,
                      noise=0.2, motion_type='KE'), dict(rs=True, motion_reg=True, motion_weights=1e2)),
+    # well-posed optima for the two-sided cost-parity test (everything covered, mild start)
+    'gs_margin': (dict(nc=4, det_per_cam=400, rolling_shutter=False, distortion=False, uncovered=-0.05,
+                       noise=0.2, perturb=0.3), dict()),
+    'rs_KE_fpk30': (dict(nc=5, det_per_cam=600, rolling_shutter=True, distortion=True, uncovered=-0.05,
+                         noise=0.2, perturb=0.3, motion_type='KE', frames_per_knot=30.0),
+                    dict(rs=True, motion_reg=True, motion_weights=1e2)),
 }
 
 

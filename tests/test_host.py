@@ -1,0 +1,101 @@
+"""Host-side logic: C-ABI library exports, loud failure without a GPU, packing round trip,
+Rodrigues helpers, the NumPy model of the device solver."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+from mvus_b200 import _cabi, hostmath
+from mvus_b200.problem import FlatProblem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, 'include', 'mvus_ba.h')).read()
+    declared = sorted(set(re.findall(r'\b(mvus_ba_\w+)\s*\(', hdr)))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(built_lib)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert sorted(_cabi.EXPORTS) == declared
+    lib.mvus_ba_version.restype = ctypes.c_char_p
+    assert b'sm_100a' in lib.mvus_ba_version()
+
+
+def test_no_cpu_fallback(built_lib):
+    """Without a CUDA device the product path must fail loudly (no silent CPU route)."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip('GPU present')
+    fl, truth, bakw = cases.make('gs_plain')
+    fp = FlatProblem(fl, fl.numCam, **bakw)
+    with pytest.raises(_cabi.MvusError, match='no usable CUDA device'):
+        _cabi.Handle(fp)
+    with pytest.raises(_cabi.MvusError):
+        fl.BA(fl.numCam)
+    import mvus_b200
+    src = ''.join(open(os.path.join(ROOT, 'mvus_b200', f)).read()
+                  for f in os.listdir(os.path.join(ROOT, 'mvus_b200')) if f.endswith('.py'))
+    assert 'import oracle' not in src and 'from oracle' not in src
+
+
+def test_pack_unpack_roundtrip():
+    for name in ('gs_plain', 'calib_KE'):
+        fl, truth, bakw = cases.make(name)
+        fp = FlatProblem(fl, fl.numCam, **bakw)
+        x = fp.x0 + 0.01
+        fp.unpack_into(fl, x)
+        fp2 = FlatProblem(fl, fl.numCam, **bakw)
+        assert np.abs(fp2.x0 - x).max() <= 1e-12
+        for c in fl.cameras:
+            assert np.allclose(c.P, c.K @ np.hstack((c.R, c.t.reshape(3, 1))), atol=1e-12, rtol=0)
+
+
+def test_rodrigues_matches_opencv():
+    cv2 = pytest.importorskip('cv2')
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        w = rng.normal(size=3) * rng.choice([1e-9, 0.1, 1.0, 3.0])
+        R = hostmath.rodrigues_to_matrix(w)
+        assert np.abs(R - cv2.Rodrigues(w)[0]).max() <= 1e-14
+        assert np.abs(hostmath.matrix_to_rodrigues(R) - cv2.Rodrigues(R)[0].ravel()).max() <= 1e-10
+
+
+def test_solver_model_matches_dense_solve():
+    """tests/proto/bcr_proto.py (the NumPy model ba_solve.cuh mirrors): cyclic reduction + Schur
+    complement == dense solve of the damped normal equations."""
+    from proto import bcr_proto
+    from oracle import ba_oracle
+    for bw, name in ((3, 'gs_plain'), (4, 'rs_F_gap'), (6, 'rs_bounds_dense')):
+        fl, truth, bakw = cases.make(name, det_per_cam=150)
+        prob = ba_oracle.Problem(fl, fl.numCam, **bakw)
+        x = prob.x0
+        J = prob.jacobian(x).toarray() * prob.free_mask()[None, :]
+        r = prob.residual(x)
+        n_ctrl = sum(prob.ncoef)
+        cols = np.zeros((n_ctrl, 3), int)
+        j = 0
+        for s in range(prob.S):
+            for l in range(prob.ncoef[s]):
+                for ax in range(3):
+                    cols[j, ax] = prob.coef_off[s] + ax * prob.ncoef[s] + l
+                j += 1
+        A, bc, D, E, Wt, perm = bcr_proto.assemble(J, r, prob.n_other, n_ctrl, cols, bw)
+        lam = 1e-3
+        dc, ds = bcr_proto.solve_bcr(A, bc, D, E, Wt, lam)
+        H = J.T @ J
+        ref = np.linalg.solve(H + lam * np.diag(np.clip(np.diag(H), 1e-6, 1e32)), -J.T @ r)
+        mine = np.zeros(prob.n)
+        mine[:prob.n_other] = dc
+        flat = ds.reshape(-1)
+        ok = perm >= 0
+        mine[perm[ok]] = flat[ok]
+        assert np.abs(mine - ref).max() <= 1e-8 * np.abs(ref).max()
