@@ -101,6 +101,12 @@ int mvus_ba_set_detections(mvus_ba_handle h, const int64_t* cam_ptr, const doubl
                            const double* x, const double* y, const double* height,
                            const double* calib);
 
+/* Same, without a host-side concatenation: one (frame, x, y) row-pointer triple per camera
+ * (rows 0/1/2 of Scene.detections[i] when they are contiguous), count[i] detections each. */
+int mvus_ba_set_detections_rows(mvus_ba_handle h, const int64_t* count, const double* const* frame,
+                                const double* const* x, const double* const* y, const double* height,
+                                const double* calib);
+
 /* Splines: Scene.spline['tck'] / ['int'] (common.py:224-270).  interval: 2*S doubles
  * (row 0 = starts, row 1 = ends, i.e. the 2 x S array flattened); knot_ptr[S+1] into
  * knots[]; degree[s] in {1,3} (common.py:247, 267).  Coefficients travel inside x. */
@@ -138,8 +144,10 @@ int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, double* r_o
                   mvus_ba_stats* stats);
 
 /* detections_global of the optimised cameras at parameters x (common.py:105-127, 695):
- * t = alpha (f + rho y/H) + beta and the (undistorted) observation; each output N long. */
-int mvus_ba_detections_global(mvus_ba_handle h, const double* x, double* t, double* u, double* v);
+ * t = alpha (f + rho y/H) + beta and the (undistorted) observation.  out[3*N]: for camera i
+ * a contiguous 3 x N_i row-major block [t; u; v] starting at 3*cam_ptr[i] -- exactly the
+ * array the reference stores in Scene.detections_global[i] (np.vstack, common.py:127). */
+int mvus_ba_detections_global(mvus_ba_handle h, const double* x, double* out);
 
 /* Diagnostics used by the parity tests: the normal equations K2 assembles at x.
  *   A    [nc*Pc*Pc]  camera diagonal blocks (Pc = 3 + C), row-major per camera

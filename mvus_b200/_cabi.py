@@ -36,7 +36,7 @@ class BAStats(ctypes.Structure):
 
 
 EXPORTS = ['mvus_ba_version', 'mvus_ba_create', 'mvus_ba_destroy', 'mvus_ba_last_error',
-           'mvus_ba_set_detections', 'mvus_ba_set_splines', 'mvus_ba_dims', 'mvus_ba_residual',
+           'mvus_ba_set_detections', 'mvus_ba_set_detections_rows', 'mvus_ba_set_splines', 'mvus_ba_dims', 'mvus_ba_residual',
            'mvus_ba_residual_jacobian', 'mvus_ba_solve', 'mvus_ba_detections_global',
            'mvus_ba_normal_equations', 'mvus_ba_nccl_unique_id', 'mvus_ba_comm_init',
            'mvus_ba_time_resjac', 'mvus_ba_time_accumulate']
@@ -64,12 +64,14 @@ def load():
     lib.mvus_ba_destroy.argtypes = [ctypes.c_void_p]
     lib.mvus_ba_destroy.restype = None
     lib.mvus_ba_set_detections.argtypes = [ctypes.c_void_p, _lp, _dp, _dp, _dp, _dp, _dp]
+    _pp = ctypes.POINTER(ctypes.c_void_p)
+    lib.mvus_ba_set_detections_rows.argtypes = [ctypes.c_void_p, _lp, _pp, _pp, _pp, _dp, _dp]
     lib.mvus_ba_set_splines.argtypes = [ctypes.c_void_p, ctypes.c_int32, _dp, _lp, _dp, _ip]
     lib.mvus_ba_dims.argtypes = [ctypes.c_void_p, _lp, _lp, _lp, _lp, _ip]
     lib.mvus_ba_residual.argtypes = [ctypes.c_void_p, _dp, _dp]
     lib.mvus_ba_residual_jacobian.argtypes = [ctypes.c_void_p, _dp, _dp, _ip, _dp, _ip, _dp]
     lib.mvus_ba_solve.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, ctypes.POINTER(BAStats)]
-    lib.mvus_ba_detections_global.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp]
+    lib.mvus_ba_detections_global.argtypes = [ctypes.c_void_p, _dp, _dp]
     lib.mvus_ba_normal_equations.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp, _ip, _dp, _dp]
     lib.mvus_ba_nccl_unique_id.argtypes = [ctypes.c_char_p]
     lib.mvus_ba_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p]
@@ -107,8 +109,10 @@ class Handle:
         rc = self.lib.mvus_ba_create(ctypes.byref(desc), ctypes.byref(self.h))
         if rc != 0:
             raise MvusError('mvus_ba_create: %s' % self.lib.mvus_ba_last_error(None).decode())
-        self._check(self.lib.mvus_ba_set_detections(self.h, _l(fp.cam_ptr), _d(fp.frame), _d(fp.x_raw),
-                                                    _d(fp.y_raw), _d(fp.height), _d(fp.calib)))
+        nc = fp.nc
+        rows = [(ctypes.c_void_p * nc)(*[int(d[k].ctypes.data) for d in fp.dets]) for k in range(3)]
+        self._check(self.lib.mvus_ba_set_detections_rows(self.h, _l(fp.N_cam), rows[0], rows[1], rows[2],
+                                                         _d(fp.height), _d(fp.calib)))
         interval = np.ascontiguousarray(fp.interval.reshape(-1))
         self._check(self.lib.mvus_ba_set_splines(self.h, fp.S, _d(interval), _l(fp.knot_ptr), _d(fp.knots),
                                                  _i(fp.degree)))
@@ -166,9 +170,11 @@ class Handle:
 
     def detections_global(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
-        t, u, v = np.empty(self.N), np.empty(self.N), np.empty(self.N)
-        self._check(self.lib.mvus_ba_detections_global(self.h, _d(x), _d(t), _d(u), _d(v)))
-        return t, u, v
+        out = np.empty(3 * self.N)
+        self._check(self.lib.mvus_ba_detections_global(self.h, _d(x), _d(out)))
+        # zero-copy 3 x N_i views, one per camera: the arrays Scene.detections_global holds
+        cp = self.fp.cam_ptr
+        return [out[3 * cp[k]:3 * cp[k + 1]].reshape(3, -1) for k in range(self.fp.nc)]
 
     def normal_equations(self, x, want_dense=True):
         fp = self.fp

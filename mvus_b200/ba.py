@@ -85,14 +85,13 @@ def detection_to_global(scene, *cam, motion_prior=False):
     fp = FlatProblem(s, len(cams))
     hd = _cabi.Handle(fp, device=DEVICE)
     try:
-        t, u, v = hd.detections_global(fp.x0)
+        dg = hd.detections_global(fp.x0)
     finally:
         hd.close()
     while len(scene.detections_global) < scene.numCam:
         scene.detections_global.append([])
     for k, i in enumerate(cams):
-        a, b = fp.cam_ptr[k], fp.cam_ptr[k + 1]
-        scene.detections_global[i] = np.vstack((t[a:b], u[a:b], v[a:b]))
+        scene.detections_global[i] = dg[k]
 
 
 def compute_visibility(scene):
@@ -119,10 +118,10 @@ def error_cam(scene, cam_id, mode='dist', motion_prior=False, norm=False):
     hd = _cabi.Handle(fp, device=DEVICE)
     try:
         r, span, _, _, _ = hd.residual_jacobian(fp.x0)
-        t, u, v = hd.detections_global(fp.x0)
+        dg = hd.detections_global(fp.x0)
     finally:
         hd.close()
-    scene.detections_global[cam_id] = np.vstack((t, u, v))
+    scene.detections_global[cam_id] = dg[0]
     N = fp.N
     eu, ev = r[:N], r[N:2 * N]
     if mode == 'each':
@@ -217,12 +216,11 @@ def bundle_adjust(scene, numCam, max_iter=10, rs=False, motion_prior=False, moti
         """detections_global (and visible) of the optimised cameras from the BA handle itself
         (one upload of the detections serves visibility, solve and refresh); cameras outside
         sequence[:numCam] go through a second, small handle."""
-        t, u, v = hd.detections_global(x)
+        new = hd.detections_global(x)
         dg = list(scene.detections_global) if len(scene.detections_global) == scene.numCam \
             else [[] for _ in range(scene.numCam)]
         for k, i in enumerate(fp.seq):
-            a, b = fp.cam_ptr[k], fp.cam_ptr[k + 1]
-            dg[i] = np.vstack((t[a:b], u[a:b], v[a:b]))
+            dg[i] = new[k]
         scene.detections_global = dg
         if others:
             detection_to_global(scene, others)

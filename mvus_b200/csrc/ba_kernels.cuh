@@ -167,20 +167,25 @@ __global__ void det_global_kernel(const double* __restrict__ camprep, const int*
                                   const double* __restrict__ frame, const double* __restrict__ xr,
                                   const double* __restrict__ yr, const double* __restrict__ obs_u,
                                   const double* __restrict__ obs_v, int calib, int undist,
-                                  double* __restrict__ t, double* __restrict__ u, double* __restrict__ v) {
+                                  const int64_t* __restrict__ row_off, double* __restrict__ out) {
     const int tl = blockIdx.x;
     if ((int)threadIdx.x >= tile_cnt[tl]) return;
-    const CamPrep& c = *reinterpret_cast<const CamPrep*>(camprep + (size_t)tile_cam[tl] * CAMPREP_DOUBLES);
+    const int cam = tile_cam[tl];
+    const CamPrep& c = *reinterpret_cast<const CamPrep*>(camprep + (size_t)cam * CAMPREP_DOUBLES);
     const int64_t d = tile_start[tl] + threadIdx.x;
-    t[d] = c.alpha * (frame[d] + c.rho * (yr[d] * c.invH)) + c.beta;
+    const int64_t c0 = row_off[cam] >> 1, ncam = (row_off[cam + 1] >> 1) - c0;
+    double* t = out + 3 * c0 + (d - c0);       // camera block: [t (ncam) | u (ncam) | v (ncam)]
+    double* u = t + ncam;
+    double* v = u + ncam;
+    *t = c.alpha * (frame[d] + c.rho * (yr[d] * c.invH)) + c.beta;
     if (calib) {
         if (undist) {
             double xn, yn;
             undistort5(xr[d], yr[d], c.K4, c.d, xn, yn);
-            u[d] = c.K4[0] * xn + c.K4[2];
-            v[d] = c.K4[1] * yn + c.K4[3];
-        } else { u[d] = xr[d]; v[d] = yr[d]; }
-    } else { u[d] = obs_u[d]; v[d] = obs_v[d]; }
+            *u = c.K4[0] * xn + c.K4[2];
+            *v = c.K4[1] * yn + c.K4[3];
+        } else { *u = xr[d]; *v = yr[d]; }
+    } else { *u = obs_u[d]; *v = obs_v[d]; }
 }
 
 }  // namespace mvus

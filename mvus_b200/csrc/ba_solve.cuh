@@ -38,8 +38,12 @@ struct K2Cfg {
     static constexpr int THREADS = 256;
     static constexpr int EPT = (NE + THREADS - 1) / THREADS;
     static constexpr int LDT = TILE_DET + 1;
-    static constexpr size_t SMEM = (size_t)(2 * (P + 1)) * LDT * sizeof(double) + TILE_DET * sizeof(int);
+    // J planes + span + run table (start, g, 4 x (kb, loc))
+    static constexpr size_t SMEM = (size_t)(2 * (P + 1)) * LDT * sizeof(double) +
+                                   (size_t)(TILE_DET + (TILE_DET + 1) + TILE_DET + 8 * TILE_DET + 8) * sizeof(int);
 };
+
+enum { K2_NONE = 0, K2_CAMCAM, K2_CAMRES, K2_CAMCTRL, K2_CTRLCTRL, K2_CTRLRES };
 
 template <int P>
 __global__ void __launch_bounds__(256)
@@ -52,11 +56,17 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
     extern __shared__ double s_mem[];
     double* s_J = s_mem;                                        // [2*(P+1)][LDT]
     int* s_span = reinterpret_cast<int*>(s_mem + (size_t)2 * (P + 1) * Cfg::LDT);
+    int* s_rstart = s_span + TILE_DET;                          // [TILE_DET + 1]
+    int* s_rg = s_rstart + TILE_DET + 1;                        // [TILE_DET]
+    int* s_kb = s_rg + TILE_DET;                                // [TILE_DET][4]
+    int* s_loc = s_kb + 4 * TILE_DET;                           // [TILE_DET][4]
+    int* s_misc = s_loc + 4 * TILE_DET;                         // [0] = number of runs, [1..4] warp counts
     const int tl = blockIdx.x, cam = tile_cam[tl], cnt = tile_cnt[tl];
     const int64_t d0 = tile_start[tl];
     const int q = 3 * bw;
+    const int tid = threadIdx.x;
     // stage: planes 0..P-1 = u row, P = r_u, P+1..2P = v row, 2P+1 = r_v
-    for (int idx = threadIdx.x; idx < 2 * (P + 1) * TILE_DET; idx += blockDim.x) {
+    for (int idx = tid; idx < 2 * (P + 1) * TILE_DET; idx += blockDim.x) {
         const int pl = idx / TILE_DET, t = idx - pl * TILE_DET;
         double v = 0.0;
         if (t < cnt) {
@@ -69,86 +79,123 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
         }
         s_J[pl * Cfg::LDT + t] = v;
     }
-    for (int t = threadIdx.x; t < TILE_DET; t += blockDim.x) s_span[t] = t < cnt ? span[d0 + t] : -1;
+    if (tid < TILE_DET) s_span[tid] = tid < cnt ? span[d0 + tid] : -2;
+    __syncthreads();
+    // run table: maximal runs of equal span index (ballot scan over the 128 tile slots)
+    if (tid < TILE_DET) {
+        const int g = s_span[tid];
+        const bool head = tid < cnt && (tid == 0 || g != s_span[tid - 1]);
+        const unsigned bal = __ballot_sync(0xffffffffu, head);
+        if ((tid & 31) == 0) s_misc[1 + (tid >> 5)] = __popc(bal);
+        __syncwarp();
+        // the 4 warps of this branch synchronise through the barrier below; compute prefix later
+        s_rg[tid] = head ? (int)(__popc(bal & ((1u << (tid & 31)) - 1u))) : -1;   // rank inside the warp
+    }
+    __syncthreads();
+    if (tid < TILE_DET) {
+        int base = 0;
+        for (int w = 0; w < (tid >> 5); ++w) base += s_misc[1 + w];
+        const int rk = s_rg[tid];
+        const int g = s_span[tid];
+        __syncwarp();
+        if (tid == 0) s_misc[0] = s_misc[1] + s_misc[2] + s_misc[3] + s_misc[4];
+        if (rk >= 0) {
+            const int ridx = base + rk;
+            s_rstart[ridx] = tid;
+            // overwrite s_rg lazily below (needs all ranks read first)
+            s_kb[ridx * 4] = g;            // stash g; expanded after the barrier
+        }
+    }
+    __syncthreads();
+    const int nruns = s_misc[0];
+    if (tid == 0) s_rstart[nruns] = cnt;
+    if (tid < nruns) {
+        const int g = s_kb[tid * 4];
+        s_rg[tid] = g;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int j = g - 3 + m;
+            int kb = -1, loc = 0;
+            if (g >= 0 && j >= 0) { kb = j / bw; loc = (j - kb * bw) * 3; }
+            s_kb[tid * 4 + m] = kb;
+            s_loc[tid * 4 + m] = loc;
+        }
+    }
     __syncthreads();
 
-    int ea[Cfg::EPT], eb[Cfg::EPT];
-    double acc[Cfg::EPT];
+    int typ[Cfg::EPT], ia[Cfg::EPT], ib[Cfg::EPT];
+    const double* pa[Cfg::EPT];
+    const double* pb[Cfg::EPT];
+    double acc[Cfg::EPT], cacc[Cfg::EPT];
 #pragma unroll
     for (int k = 0; k < Cfg::EPT; ++k) {
-        int e = threadIdx.x + k * Cfg::THREADS;
-        ea[k] = -1; eb[k] = -1; acc[k] = 0.0;
+        int e = tid + k * Cfg::THREADS;
+        typ[k] = K2_NONE; ia[k] = 0; ib[k] = 0; acc[k] = 0.0; cacc[k] = 0.0;
+        pa[k] = s_J; pb[k] = s_J;
         if (e < Cfg::NE) {
             int a = 0;
             while (e >= (P + 1 - a)) { e -= (P + 1 - a); ++a; }
-            ea[k] = a; eb[k] = a + e;
+            const int b = a + e;
+            pa[k] = s_J + a * Cfg::LDT; pb[k] = s_J + b * Cfg::LDT;
+            ia[k] = a; ib[k] = b;
+            if (a < Pc) typ[k] = b < Pc ? K2_CAMCAM : (b == P ? K2_CAMRES : K2_CAMCTRL);
+            else if (a < P) typ[k] = b == P ? K2_CTRLRES : K2_CTRLCTRL;
         }
     }
-    auto flush_ctrl = [&](int g) {
+    constexpr int VOFF = (P + 1) * Cfg::LDT;
+    for (int rr = 0; rr < nruns; ++rr) {
+        const int t0 = s_rstart[rr], t1 = s_rstart[rr + 1];
+        if (s_rg[rr] < 0) continue;              // uncovered detections: zero rows
 #pragma unroll
         for (int k = 0; k < Cfg::EPT; ++k) {
-            const int a = ea[k], b = eb[k];
-            if (a < 0 || a >= P || b < Pc || (b == P && a < Pc)) continue;   // not a control-point entry
+            double s = 0.0;
+            const double* qa = pa[k];
+            const double* qb = pb[k];
+            for (int t = t0; t < t1; ++t) s = fma(qa[t], qb[t], fma(qa[VOFF + t], qb[VOFF + t], s));
+            acc[k] = s;
+        }
+        // flush control-point entries of this run
+#pragma unroll
+        for (int k = 0; k < Cfg::EPT; ++k) {
+            const int ty = typ[k];
             const double v = acc[k];
-            acc[k] = 0.0;
+            if (ty <= K2_CAMRES) { cacc[k] += v; continue; }
             if (v == 0.0) continue;
-            if (b == P) {                    // control x residual -> rhs column (b = -g)
+            const int a = ia[k], b = ib[k];
+            if (ty == K2_CAMCTRL) {
+                const int mb = (b - Pc) / 3, bx = (b - Pc) - mb * 3;
+                const int kb = s_kb[rr * 4 + mb];
+                if (kb >= 0) atomicAdd(W + ((int64_t)kb * q + s_loc[rr * 4 + mb] + bx) * ldw + cam * Pc + a, v);
+            } else if (ty == K2_CTRLRES) {
                 const int ma = (a - Pc) / 3, ax = (a - Pc) - ma * 3;
-                const int j = g - 3 + ma;
-                if (j < 0) continue;
-                const int kb = j / bw;
-                atomicAdd(W + ((int64_t)kb * q + (j - kb * bw) * 3 + ax) * ldw + (ldw - 1), -v);
-                continue;
-            }
-            const int mb = (b - Pc) / 3, bx = (b - Pc) - mb * 3;
-            const int jb = g - 3 + mb;
-            if (jb < 0) continue;
-            const int kbb = jb / bw, lb = (jb - kbb * bw) * 3 + bx;
-            if (a < Pc) {                    // camera x control -> W
-                atomicAdd(W + ((int64_t)kbb * q + lb) * ldw + cam * Pc + a, v);
-                continue;
-            }
-            const int ma = (a - Pc) / 3, ax = (a - Pc) - ma * 3;
-            const int ja = g - 3 + ma;
-            if (ja < 0) continue;
-            const int kba = ja / bw, la = (ja - kba * bw) * 3 + ax;
-            if (kba == kbb) {
-                atomicAdd(D + ((int64_t)kba * q + la) * q + lb, v);
-                if (la != lb) atomicAdd(D + ((int64_t)kba * q + lb) * q + la, v);
+                const int kb = s_kb[rr * 4 + ma];
+                if (kb >= 0) atomicAdd(W + ((int64_t)kb * q + s_loc[rr * 4 + ma] + ax) * ldw + (ldw - 1), -v);
             } else {
-                atomicAdd(E + ((int64_t)kba * q + la) * q + lb, v);
+                const int ma = (a - Pc) / 3, ax = (a - Pc) - ma * 3;
+                const int mb = (b - Pc) / 3, bx = (b - Pc) - mb * 3;
+                const int kba = s_kb[rr * 4 + ma], kbb = s_kb[rr * 4 + mb];
+                if (kba < 0 || kbb < 0) continue;
+                const int la = s_loc[rr * 4 + ma] + ax, lb = s_loc[rr * 4 + mb] + bx;
+                if (kba == kbb) {
+                    atomicAdd(D + ((int64_t)kba * q + la) * q + lb, v);
+                    if (la != lb) atomicAdd(D + ((int64_t)kba * q + lb) * q + la, v);
+                } else {
+                    atomicAdd(E + ((int64_t)kba * q + la) * q + lb, v);
+                }
             }
-        }
-    };
-    int gprev = -1;
-    for (int t = 0; t < cnt; ++t) {
-        const int g = s_span[t];
-        if (g != gprev) {
-            if (gprev >= 0) flush_ctrl(gprev);
-            gprev = g;
-        }
-        if (g < 0) continue;
-#pragma unroll
-        for (int k = 0; k < Cfg::EPT; ++k) {
-            if (ea[k] < 0) continue;
-            const double* ja = s_J + ea[k] * Cfg::LDT + t;
-            const double* jb = s_J + eb[k] * Cfg::LDT + t;
-            acc[k] = fma(ja[0], jb[0], fma(ja[(P + 1) * Cfg::LDT], jb[(P + 1) * Cfg::LDT], acc[k]));
         }
     }
-    if (gprev >= 0) flush_ctrl(gprev);
-    // camera-only entries
+    // camera-only entries: once per tile
 #pragma unroll
     for (int k = 0; k < Cfg::EPT; ++k) {
-        const int a = ea[k], b = eb[k];
-        if (a < 0 || a >= Pc) continue;
-        if (b < Pc) {
-            const double v = acc[k];
-            if (v == 0.0) continue;
+        const double v = cacc[k];
+        if (v == 0.0) continue;
+        const int a = ia[k], b = ib[k];
+        if (typ[k] == K2_CAMCAM) {
             atomicAdd(A + ((int64_t)cam * Pc + a) * Pc + b, v);
             if (a != b) atomicAdd(A + ((int64_t)cam * Pc + b) * Pc + a, v);
-        } else if (b == P) {
-            if (acc[k] != 0.0) atomicAdd(bc + cam * Pc + a, -acc[k]);
+        } else if (typ[k] == K2_CAMRES) {
+            atomicAdd(bc + cam * Pc + a, -v);
         }
     }
 }
@@ -242,7 +289,7 @@ __global__ void floor_kernel(double* __restrict__ v, int64_t n, const double* __
 //   - if j is an odd multiple of s (or the root pass): factor D_j, form ZL/ZR/W~ rows.
 // ZR is stored in E[j]; root = final pass on block 0.
 template <int Q>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* __restrict__ Dw,
                  double* __restrict__ Ew, double* __restrict__ Ww, double* __restrict__ ZL,
                  int* __restrict__ fail_flag) {
@@ -257,6 +304,7 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* _
     const int qq = q * q;
     const bool has_m = sp > 0 && j - sp >= 0 && (((j - sp) / sp) & 1);
     const bool has_p = sp > 0 && j + sp < nb && (((j + sp) / sp) & 1);
+#pragma unroll 1
     for (int i = tid; i < qq; i += nt) {
         Dj[i] = Dw[j * qq + i];
         zl_m[i] = has_m ? ZL[(j - sp) * qq + i] : 0.0;
@@ -267,9 +315,11 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* _
     if (tid == 0) s_bad = 0;
     __syncthreads();
     // D_j -= ZR_m^T ZR_m + ZL_p^T ZL_p ; couplings of the eliminated block
+#pragma unroll 1
     for (int i = tid; i < qq; i += nt) {
         const int a = i / q, b = i - a * q;
         double acc = 0.0, el = 0.0, er = 0.0;
+#pragma unroll 1
         for (int k = 0; k < q; ++k) {
             acc += zr_m[k * q + a] * zr_m[k * q + b] + zl_p[k * q + a] * zl_p[k * q + b];
             el -= zr_m[k * q + a] * zl_m[k * q + b];      // rows j, cols j - s   (bridge through j - sp)
@@ -279,6 +329,7 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* _
     }
     if (sp == 0 && elim && !root) {
         // level 0: original couplings.  E[j-1] has rows j-1, cols j -> transpose; E[j] rows j, cols j+1
+#pragma unroll 1
         for (int i = tid; i < qq; i += nt) {
             const int a = i / q, b = i - a * q;
             El[i] = Ew[(j - 1) * qq + b * q + a];
@@ -289,34 +340,43 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* _
     if (elim) {
         // Cholesky of Dj (lower, in place), q <= 18: one warp, column by column
         if (tid < 32) {
+#pragma unroll 1
             for (int c = 0; c < q; ++c) {
                 double d = Dj[c * q + c];
                 if (!(d > 0.0)) { if (tid == 0) s_bad = 1; d = 1.0; }
                 d = sqrt(d);
                 __syncwarp();
                 if (tid == 0) Dj[c * q + c] = d;
+#pragma unroll 1
                 for (int i = c + 1 + tid; i < q; i += 32) Dj[i * q + c] /= d;
                 __syncwarp();
+#pragma unroll 1
                 for (int i = c + 1 + tid; i < q; i += 32)
+#pragma unroll 1
                     for (int k = c + 1; k <= i; ++k) Dj[i * q + k] -= Dj[i * q + c] * Dj[k * q + c];
                 __syncwarp();
             }
         }
         __syncthreads();
         // ZL = L^-1 El, ZR = L^-1 Er : thread per column of [El | Er]
+#pragma unroll 1
         for (int c = tid; c < 2 * q; c += nt) {
             double* Mx = c < q ? El : Er;
             const int cc = c < q ? c : c - q;
+#pragma unroll 1
             for (int i = 0; i < q; ++i) {
                 double v = Mx[i * q + cc];
+#pragma unroll 1
                 for (int k = 0; k < i; ++k) v -= Dj[i * q + k] * Mx[k * q + cc];
                 Mx[i * q + cc] = v / Dj[i * q + i];
             }
         }
         __syncthreads();
         if (!root)
+#pragma unroll 1
             for (int i = tid; i < qq; i += nt) { ZL[j * qq + i] = El[i]; Ew[j * qq + i] = Er[i]; }
     }
+#pragma unroll 1
     for (int i = tid; i < qq; i += nt) Dw[j * qq + i] = Dj[i];
     // W~ columns: pending update, then forward substitution if eliminated
     const double* Wm = Ww + (j - sp) * (int64_t)q * ldw;
@@ -327,14 +387,14 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* _
 #pragma unroll
         for (int a = 0; a < Q; ++a) w[a] = Wj[(int64_t)a * ldw + c];
         if (has_m)
-#pragma unroll 3
+#pragma unroll 1
             for (int k = 0; k < Q; ++k) {
                 const double x = Wm[(int64_t)k * ldw + c];
 #pragma unroll
                 for (int a = 0; a < Q; ++a) w[a] -= zr_m[k * Q + a] * x;
             }
         if (has_p)
-#pragma unroll 3
+#pragma unroll 1
             for (int k = 0; k < Q; ++k) {
                 const double x = Wp[(int64_t)k * ldw + c];
 #pragma unroll
@@ -343,6 +403,7 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* _
         if (elim) {
 #pragma unroll
             for (int i = 0; i < Q; ++i) {
+                asm volatile("" ::: "memory");      // keep row i's L loads inside iteration i (registers)
                 double v = w[i];
 #pragma unroll
                 for (int k = 0; k < i; ++k) v -= Dj[i * Q + k] * w[k];
@@ -356,45 +417,60 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* _
 }
 
 // S~ = sum over rows of W~^T W~ (lower-triangle tiles), FP64 SYRK with split-K + atomics.
-// grid = (tile pairs, K slabs), block = 16x16, 4x4 micro-tile, 64x64 output tile.
+// grid = (tile pairs ti >= tj, K slabs), 256 threads, 128x128 output tile, 8x8 register
+// micro-tile per thread with a STRIDED column mapping (thread (tx,ty) owns rows ty+16*i and
+// columns tx+16*j): every shared-memory read of the B panel is unit-stride across the warp and
+// every read of the A panel is a broadcast -> no bank conflicts (the first version, 4x4
+// contiguous micro-tiles, measured 86 M conflicts and 4.4 TFLOP/s, profiles/r1_notes.md).
+constexpr int SY_T = 128, SY_K = 16;
 __global__ void __launch_bounds__(256)
-syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int nt_side, int slab,
-            double* __restrict__ Sfull) {
-    __shared__ double As[16][64 + 1], Bs[16][64 + 1];
-    // decode tile pair (ti >= tj)
+syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int slab, double* __restrict__ Sfull) {
+    __shared__ double As[SY_K][SY_T], Bs[SY_K][SY_T];
     int p = blockIdx.x, ti = 0;
     while (p >= ti + 1) { p -= ti + 1; ++ti; }
     const int tj = p;
     const int64_t r0 = (int64_t)blockIdx.y * slab;
     const int64_t r1 = r0 + slab < R ? r0 + slab : R;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double acc[4][4] = {};
-    for (int64_t rr = r0; rr < r1; rr += 16) {
-        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-            const int kk = i >> 6, cc = i & 63;
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+    const bool diag = (ti == tj);
+    for (int64_t rr = r0; rr < r1; rr += SY_K) {
+        // 16 rows x 128 columns per panel: thread loads 8 elements of each panel
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int idx = threadIdx.x + k * 256;
+            const int kk = idx >> 7, cc = idx & 127;
             const int64_t row = rr + kk;
-            const int ca = ti * 64 + cc, cb = tj * 64 + cc;
-            As[kk][cc] = (row < r1 && ca < ldw) ? Ww[row * ldw + ca] : 0.0;
-            Bs[kk][cc] = (row < r1 && cb < ldw) ? Ww[row * ldw + cb] : 0.0;
+            const int ca = ti * SY_T + cc, cb = tj * SY_T + cc;
+            const bool inr = row < r1;
+            As[kk][cc] = (inr && ca < ldw) ? Ww[row * ldw + ca] : 0.0;
+            if (!diag) Bs[kk][cc] = (inr && cb < ldw) ? Ww[row * ldw + cb] : 0.0;
         }
         __syncthreads();
+        const double (*Bp)[SY_T] = diag ? As : Bs;
+#pragma unroll 4
+        for (int kk = 0; kk < SY_K; ++kk) {
+            double a[8], b[8];
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            double a[4], b[4];
+            for (int i = 0; i < 8; ++i) { a[i] = As[kk][ty + 16 * i]; b[i] = Bp[kk][tx + 16 * i]; }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int jx = 0; jx < 4; ++jx) acc[i][jx] = fma(a[i], b[jx], acc[i][jx]);
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
-    for (int i = 0; i < 4; ++i)
-        for (int jx = 0; jx < 4; ++jx) {
-            const int row = ti * 64 + ty * 4 + i, col = tj * 64 + tx * 4 + jx;
-            if (row < ldw && col < ldw && col <= row && acc[i][jx] != 0.0)
-                atomicAdd(Sfull + (int64_t)row * ldw + col, acc[i][jx]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int row = ti * SY_T + ty + 16 * i, col = tj * SY_T + tx + 16 * j;
+            if (row < ldw && col <= row && acc[i][j] != 0.0)
+                atomicAdd(Sfull + (int64_t)row * ldw + col, acc[i][j]);
         }
 }
 
@@ -417,59 +493,156 @@ __global__ void form_schur_kernel(const double* __restrict__ A, const double* __
     Sfull[(int64_t)row * ldw + col] = v;
 }
 
-// Dense Cholesky + solve of the reduced camera system (n = nc*Pc <= 1152), one CTA.
-// Right-looking, lower triangle in global memory (L2 resident).  x = S^-1 rhs.
-__global__ void __launch_bounds__(1024)
-dense_chol_solve_kernel(double* __restrict__ S, int lds, int n, double* __restrict__ rhs,
-                        double* __restrict__ xout, int* __restrict__ fail_flag) {
-    __shared__ double s_col[1152];
-    __shared__ int s_bad;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    if (tid == 0) s_bad = 0;
+// Dense Cholesky + solve of the reduced camera system (n = nc*Pc <= 1152): right-looking blocked
+// factorisation, panel width 32, three small kernels per panel (diagonal block on one CTA,
+// panel solve and trailing update spread over the grid), then a blocked forward/backward
+// substitution on one CTA.  Lower triangle, leading dimension lds, in place.
+constexpr int CH_B = 32;
+__global__ void __launch_bounds__(CH_B * CH_B)
+chol_diag_kernel(double* __restrict__ S, int lds, int n, int p0, int* __restrict__ fail_flag) {
+    __shared__ double L[CH_B][CH_B + 1];
+    const int r = threadIdx.y, c = threadIdx.x;
+    const int nb = min(CH_B, n - p0);
+    L[r][c] = (r < nb && c < nb && c <= r) ? S[(int64_t)(p0 + r) * lds + p0 + c] : (r == c ? 1.0 : 0.0);
     __syncthreads();
-    for (int j = 0; j < n; ++j) {
-        double d = S[(int64_t)j * lds + j];
-        if (!(d > 0.0)) { if (tid == 0) s_bad = 1; d = 1.0; }
-        d = sqrt(d);
-        const double id = 1.0 / d;
-        for (int i = j + tid; i < n; i += nt) {
-            const double v = (i == j) ? d : S[(int64_t)i * lds + j] * id;
-            s_col[i] = v;
-            S[(int64_t)i * lds + j] = v;
+    for (int j = 0; j < nb; ++j) {
+        if (r == j && c == j) {
+            double d = L[j][j];
+            if (!(d > 0.0)) { atomicExch(fail_flag, 1); d = 1.0; }
+            L[j][j] = sqrt(d);
         }
         __syncthreads();
-        // trailing update: rows i > j, cols j < k <= i ; flatten over (i,k)
-        const int mrem = n - j - 1;
-        const int64_t tot = (int64_t)mrem * (mrem + 1) / 2;
-        for (int64_t e = tid; e < tot; e += nt) {
-            // row-major lower-triangle index -> (ii, kk), ii >= kk
-            int ii = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
-            while ((int64_t)(ii + 1) * (ii + 2) / 2 <= e) ++ii;
-            while ((int64_t)ii * (ii + 1) / 2 > e) --ii;
-            const int kk = (int)(e - (int64_t)ii * (ii + 1) / 2);
-            const int i = j + 1 + ii, k = j + 1 + kk;
-            S[(int64_t)i * lds + k] -= s_col[i] * s_col[k];
+        if (c == j && r > j) L[r][j] /= L[j][j];
+        __syncthreads();
+        if (c > j && c <= r) L[r][c] -= L[r][j] * L[c][j];
+        __syncthreads();
+    }
+    if (r < nb && c < nb && c <= r) S[(int64_t)(p0 + r) * lds + p0 + c] = L[r][c];
+}
+
+// rows below the panel: X L_pp^T = S_ip  ->  one warp per row block of 32 rows, thread = row
+__global__ void __launch_bounds__(CH_B)
+chol_panel_kernel(double* __restrict__ S, int lds, int n, int p0) {
+    __shared__ double L[CH_B][CH_B + 1];
+    const int nb = min(CH_B, n - p0);
+    for (int i = threadIdx.x; i < CH_B * CH_B; i += CH_B) {
+        const int r = i / CH_B, c = i - r * CH_B;
+        L[r][c] = (r < nb && c <= r) ? S[(int64_t)(p0 + r) * lds + p0 + c] : 0.0;
+    }
+    __syncthreads();
+    const int row = p0 + nb + blockIdx.x * CH_B + threadIdx.x;
+    if (row >= n) return;
+    double x[CH_B];
+    double* sr = S + (int64_t)row * lds + p0;
+#pragma unroll
+    for (int c = 0; c < CH_B; ++c) x[c] = c < nb ? sr[c] : 0.0;
+#pragma unroll
+    for (int c = 0; c < CH_B; ++c) {
+        if (c < nb) {
+            double v = x[c];
+#pragma unroll
+            for (int k = 0; k < c; ++k) v -= x[k] * L[c][k];
+            x[c] = v / L[c][c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CH_B; ++c) if (c < nb) sr[c] = x[c];
+}
+
+// trailing update S_ij -= L_ip L_jp^T for 32x32 tiles i >= j below the panel
+__global__ void __launch_bounds__(CH_B * 8)
+chol_update_kernel(double* __restrict__ S, int lds, int n, int p0) {
+    __shared__ double Li[CH_B][CH_B + 1], Lj[CH_B][CH_B + 1];
+    const int nb = min(CH_B, n - p0);
+    int p = blockIdx.x, ti = 0;
+    while (p >= ti + 1) { p -= ti + 1; ++ti; }
+    const int tj = p;
+    const int i0 = p0 + nb + ti * CH_B, j0 = p0 + nb + tj * CH_B;
+    for (int i = threadIdx.x; i < CH_B * CH_B; i += blockDim.x) {
+        const int r = i / CH_B, c = i - r * CH_B;
+        Li[r][c] = (i0 + r < n && c < nb) ? S[(int64_t)(i0 + r) * lds + p0 + c] : 0.0;
+        Lj[r][c] = (j0 + r < n && c < nb) ? S[(int64_t)(j0 + r) * lds + p0 + c] : 0.0;
+    }
+    __syncthreads();
+    const int c = threadIdx.x & 31, rq = threadIdx.x >> 5;      // 8 row groups of 4 rows
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = rq * 4 + k;
+        const int gi = i0 + r, gj = j0 + c;
+        if (gi < n && gj < n && gj <= gi) {
+            double acc = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < CH_B; ++kk) acc += Li[r][kk] * Lj[c][kk];
+            S[(int64_t)gi * lds + gj] -= acc;
+        }
+    }
+}
+
+// x = (L L^T)^-1 rhs, blocked by 32, one CTA of 1024 threads
+__global__ void __launch_bounds__(1024)
+chol_solve_kernel(const double* __restrict__ S, int lds, int n, double* __restrict__ rhs,
+                  double* __restrict__ xout) {
+    __shared__ double y[1152];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < n; i += nt) y[i] = rhs[i];
+    __syncthreads();
+    for (int p0 = 0; p0 < n; p0 += CH_B) {            // forward
+        const int nb = min(CH_B, n - p0);
+        if (tid < 32) {
+            for (int j = 0; j < nb; ++j) {
+                const double yj = y[p0 + j] / S[(int64_t)(p0 + j) * lds + p0 + j];
+                __syncwarp();
+                if (tid == 0) y[p0 + j] = yj;
+                if (tid > j && tid < nb) y[p0 + tid] -= S[(int64_t)(p0 + tid) * lds + p0 + j] * yj;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int i = p0 + nb + tid; i < n; i += nt) {
+            const double* sr = S + (int64_t)i * lds + p0;
+            double acc = 0.0;
+            for (int k = 0; k < nb; ++k) acc += sr[k] * y[p0 + k];
+            y[i] -= acc;
         }
         __syncthreads();
     }
-    // forward: L y = rhs (column oriented)
-    for (int j = 0; j < n; ++j) {
-        if (tid == 0) rhs[j] = rhs[j] / S[(int64_t)j * lds + j];
+    for (int p0 = ((n - 1) / CH_B) * CH_B; p0 >= 0; p0 -= CH_B) {     // backward
+        const int nb = min(CH_B, n - p0);
+        if (tid < 32) {
+            for (int j = nb - 1; j >= 0; --j) {
+                const double xj = y[p0 + j] / S[(int64_t)(p0 + j) * lds + p0 + j];
+                __syncwarp();
+                if (tid == 0) y[p0 + j] = xj;
+                if (tid < j) y[p0 + tid] -= S[(int64_t)(p0 + j) * lds + p0 + tid] * xj;
+                __syncwarp();
+            }
+        }
         __syncthreads();
-        const double yj = rhs[j];
-        for (int i = j + 1 + tid; i < n; i += nt) rhs[i] -= S[(int64_t)i * lds + j] * yj;
+        for (int i = tid; i < p0; i += nt) {
+            double acc = 0.0;
+            for (int k = 0; k < nb; ++k) acc += S[(int64_t)(p0 + k) * lds + i] * y[p0 + k];
+            y[i] -= acc;
+        }
         __syncthreads();
     }
-    // backward: L^T x = y
-    for (int j = n - 1; j >= 0; --j) {
-        if (tid == 0) rhs[j] = rhs[j] / S[(int64_t)j * lds + j];
-        __syncthreads();
-        const double xj = rhs[j];
-        for (int i = tid; i < j; i += nt) rhs[i] -= S[(int64_t)j * lds + i] * xj;
-        __syncthreads();
+    for (int i = tid; i < n; i += nt) xout[i] = y[i];
+}
+
+inline void dense_chol_solve(mvus_ba_ctx* h, double* S, int lds, int n, double* rhs, double* xout, int* fail_flag) {
+    for (int p0 = 0; p0 < n; p0 += CH_B) {
+        const int nb = std::min(CH_B, n - p0);
+        chol_diag_kernel<<<1, dim3(CH_B, CH_B), 0, h->st>>>(S, lds, n, p0, fail_flag);
+        h->launches++;
+        const int rem = n - p0 - nb;
+        if (rem > 0) {
+            const int nblk = (rem + CH_B - 1) / CH_B;
+            chol_panel_kernel<<<nblk, CH_B, 0, h->st>>>(S, lds, n, p0);
+            chol_update_kernel<<<nblk * (nblk + 1) / 2, CH_B * 8, 0, h->st>>>(S, lds, n, p0);
+            h->launches += 2;
+        }
     }
-    for (int i = tid; i < n; i += nt) xout[i] = rhs[i];
-    if (tid == 0 && s_bad) atomicExch(fail_flag, 1);
+    chol_solve_kernel<<<1, 1024, 0, h->st>>>(S, lds, n, rhs, xout);
+    h->launches++;
 }
 
 // v[k][a] = W~[k][a][ncP] - W~[k][a][0:ncP] . dc     (one warp per row)
@@ -741,14 +914,16 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
     launch_level(h, 1, levels.empty() ? 1 : levels.back() * 2, levels.empty() ? 0 : levels.back(), 1, fail_flag);
     // Schur complement
     MV_CUDA(h, cudaMemsetAsync(h->Sd.p, 0, h->Sd.bytes(), h->st));
-    const int nts = (ldw + 63) / 64;
-    const int slab = 512;
-    dim3 g(nts * (nts + 1) / 2, (unsigned)((nbq + slab - 1) / slab));
-    syrk_kernel<<<g, 256, 0, h->st>>>(h->Ww.p, nbq, ldw, nts, slab, h->Sd.p);
+    const int nts = (ldw + SY_T - 1) / SY_T, npairs = nts * (nts + 1) / 2;
+    // ~4 waves of CTAs over the SMs, slabs a multiple of the K chunk
+    int64_t nslab = std::max<int64_t>(1, (4 * h->sm_count + npairs - 1) / npairs);
+    int slab = (int)std::max<int64_t>(256, ((nbq + nslab - 1) / nslab + SY_K - 1) / SY_K * SY_K);
+    dim3 g(npairs, (unsigned)((nbq + slab - 1) / slab));
+    syrk_kernel<<<g, 256, 0, h->st>>>(h->Ww.p, nbq, ldw, slab, h->Sd.p);
     form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
         h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->Sd.p, rhs);
-    dense_chol_solve_kernel<<<1, 1024, 0, h->st>>>(h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
-    h->launches += 3;
+    h->launches += 2;
+    dense_chol_solve(h, h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
     // back substitution
     wdc_kernel<<<(int)((nbq * 32 + 255) / 256), 256, 0, h->st>>>(h->Ww.p, h->dlt_c.p, nbq, ldw, h->dlt_s.p);
     bcr_back_kernel<<<1, 32, 0, h->st>>>(nb, q, 0, 1, h->Dw.p, h->Ew.p, h->ZL.p, h->dlt_s.p);

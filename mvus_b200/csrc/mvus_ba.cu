@@ -68,7 +68,7 @@ extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
                     &h->int_b, &h->knots, &h->spanpoly, &h->span_t0, &h->lut_t0, &h->lut_invh, &h->tau,
                     &h->x, &h->x_trial, &h->camprep, &h->r, &h->J, &h->mJ, &h->partial, &h->A, &h->D, &h->E,
                     &h->W, &h->Dw, &h->Ew, &h->Ww, &h->ZL, &h->Sd, &h->dlt_c, &h->dlt_s, &h->diag_c,
-                    &h->diag_s, &h->gvec, &h->xs})
+                    &h->diag_s, &h->gvec, &h->xs, &h->scratch})
         b->release();
     for (auto* b : {&h->row_off, &h->tile_start, &h->knot_off, &h->ctrl_off, &h->xoff, &h->lut_off}) b->release();
     for (auto* b : {&h->tile_cam, &h->tile_cnt, &h->ncoef, &h->deg, &h->lut_n, &h->lut, &h->tau_spl, &h->span,
@@ -97,22 +97,31 @@ static int finish_dims(mvus_ba_ctx* h) {
     return MVUS_OK;
 }
 
-extern "C" int mvus_ba_set_detections(mvus_ba_handle h, const int64_t* cam_ptr, const double* frame,
-                                      const double* x, const double* y, const double* height,
-                                      const double* calib) {
-    if (!h || !cam_ptr || !height || !calib) return fail(h, MVUS_ERR_ARG, "null argument");
+static int set_detections_core(mvus_ba_ctx* h, const int64_t* count, const double* const* frame,
+                               const double* const* x, const double* const* y, const double* height,
+                               const double* calib) {
     MV_CUDA(h, cudaSetDevice(h->desc.device));
     const int nc = h->nc;
-    if (cam_ptr[0] != 0) return fail(h, MVUS_ERR_ARG, "cam_ptr[0] must be 0");
-    for (int i = 0; i < nc; ++i)
-        if (cam_ptr[i + 1] < cam_ptr[i]) return fail(h, MVUS_ERR_ARG, "cam_ptr must be non-decreasing");
-    h->cam_ptr.assign(cam_ptr, cam_ptr + nc + 1);
+    std::vector<int64_t> cam_ptr(nc + 1, 0);
+    for (int i = 0; i < nc; ++i) {
+        if (count[i] < 0) return fail(h, MVUS_ERR_ARG, "negative detection count");
+        cam_ptr[i + 1] = cam_ptr[i] + count[i];
+    }
+    h->cam_ptr = cam_ptr;
     h->N = cam_ptr[nc];
-    if (h->N > 0 && (!frame || !x || !y)) return fail(h, MVUS_ERR_ARG, "null detection arrays");
     if (h->N >= (int64_t)1 << 31) return fail(h, MVUS_ERR_UNSUPPORTED, "more than 2^31 detections per handle");
-    MV_CUDA(h, upload(h->frame, frame, (size_t)h->N, h->st));
-    MV_CUDA(h, upload(h->xr, x, (size_t)h->N, h->st));
-    MV_CUDA(h, upload(h->yr, y, (size_t)h->N, h->st));
+    const size_t na = h->N > 0 ? (size_t)h->N : 1;
+    MV_CUDA(h, h->frame.alloc(na));
+    MV_CUDA(h, h->xr.alloc(na));
+    MV_CUDA(h, h->yr.alloc(na));
+    for (int i = 0; i < nc; ++i) {
+        if (count[i] == 0) continue;
+        if (!frame[i] || !x[i] || !y[i]) return fail(h, MVUS_ERR_ARG, "null detection arrays");
+        const size_t nb = (size_t)count[i] * sizeof(double);
+        MV_CUDA(h, cudaMemcpyAsync(h->frame.p + cam_ptr[i], frame[i], nb, cudaMemcpyHostToDevice, h->st));
+        MV_CUDA(h, cudaMemcpyAsync(h->xr.p + cam_ptr[i], x[i], nb, cudaMemcpyHostToDevice, h->st));
+        MV_CUDA(h, cudaMemcpyAsync(h->yr.p + cam_ptr[i], y[i], nb, cudaMemcpyHostToDevice, h->st));
+    }
     MV_CUDA(h, upload(h->height, height, (size_t)nc, h->st));
     MV_CUDA(h, upload(h->calib, calib, (size_t)nc * 9, h->st));
     std::vector<int64_t> row_off(nc + 1);
@@ -131,8 +140,8 @@ extern "C" int mvus_ba_set_detections(mvus_ba_handle h, const int64_t* cam_ptr, 
     MV_CUDA(h, upload(h->tile_cam, tcam, h->st));
     MV_CUDA(h, upload(h->tile_start, tstart, h->st));
     MV_CUDA(h, upload(h->tile_cnt, tcnt, h->st));
-    MV_CUDA(h, h->obs_u.alloc(h->N > 0 ? h->N : 1));
-    MV_CUDA(h, h->obs_v.alloc(h->N > 0 ? h->N : 1));
+    MV_CUDA(h, h->obs_u.alloc(na));
+    MV_CUDA(h, h->obs_v.alloc(na));
     if (!h->desc.opt_calib && h->n_tiles > 0) {
         observe_kernel<<<h->n_tiles, TILE_DET, 0, h->st>>>(h->tile_cam.p, h->tile_start.p, h->tile_cnt.p,
                                                           h->calib.p, h->desc.undist_points, h->xr.p, h->yr.p,
@@ -142,6 +151,32 @@ extern "C" int mvus_ba_set_detections(mvus_ba_handle h, const int64_t* cam_ptr, 
     MV_CUDA(h, cudaStreamSynchronize(h->st));
     h->have_det = true;
     return finish_dims(h);
+}
+
+extern "C" int mvus_ba_set_detections_rows(mvus_ba_handle h, const int64_t* count, const double* const* frame,
+                                           const double* const* x, const double* const* y,
+                                           const double* height, const double* calib) {
+    if (!h || !count || !frame || !x || !y || !height || !calib) return fail(h, MVUS_ERR_ARG, "null argument");
+    return set_detections_core(h, count, frame, x, y, height, calib);
+}
+
+extern "C" int mvus_ba_set_detections(mvus_ba_handle h, const int64_t* cam_ptr, const double* frame,
+                                      const double* x, const double* y, const double* height,
+                                      const double* calib) {
+    if (!h || !cam_ptr || !height || !calib) return fail(h, MVUS_ERR_ARG, "null argument");
+    const int nc = h->nc;
+    if (cam_ptr[0] != 0) return fail(h, MVUS_ERR_ARG, "cam_ptr[0] must be 0");
+    std::vector<int64_t> count(nc);
+    std::vector<const double*> pf(nc), px(nc), py(nc);
+    for (int i = 0; i < nc; ++i) {
+        if (cam_ptr[i + 1] < cam_ptr[i]) return fail(h, MVUS_ERR_ARG, "cam_ptr must be non-decreasing");
+        count[i] = cam_ptr[i + 1] - cam_ptr[i];
+        if (count[i] > 0 && (!frame || !x || !y)) return fail(h, MVUS_ERR_ARG, "null detection arrays");
+        pf[i] = frame ? frame + cam_ptr[i] : nullptr;
+        px[i] = x ? x + cam_ptr[i] : nullptr;
+        py[i] = y ? y + cam_ptr[i] : nullptr;
+    }
+    return set_detections_core(h, count.data(), pf.data(), px.data(), py.data(), height, calib);
 }
 
 extern "C" int mvus_ba_set_splines(mvus_ba_handle h, int32_t S, const double* interval,
@@ -290,28 +325,22 @@ extern "C" int mvus_ba_residual_jacobian(mvus_ba_handle h, const double* x, doub
     return check_motion_flag(h);
 }
 
-extern "C" int mvus_ba_detections_global(mvus_ba_handle h, const double* x, double* t, double* u, double* v) {
+extern "C" int mvus_ba_detections_global(mvus_ba_handle h, const double* x, double* out) {
     int rc = check_ready(h);
     if (rc) return rc;
-    if (!x || !t || !u || !v) return fail(h, MVUS_ERR_ARG, "null argument");
+    if (!x || !out) return fail(h, MVUS_ERR_ARG, "null argument");
     if (h->N == 0) return MVUS_OK;
     MV_CUDA(h, cudaMemcpyAsync(h->x.p, x, h->n * sizeof(double), cudaMemcpyHostToDevice, h->st));
     cam_prep_kernel<<<(h->nc + 63) / 64, 64, 0, h->st>>>(h->x.p, h->nc, h->C, h->desc.opt_calib, h->calib.p,
                                                          h->height.p, h->camprep.p);
-    // reuse r / J storage as scratch for the three outputs
-    DevBuf<double> tmp;
-    MV_CUDA(h, tmp.alloc((size_t)3 * h->N));
+    MV_CUDA(h, h->scratch.alloc((size_t)3 * h->N));
     det_global_kernel<<<h->n_tiles, TILE_DET, 0, h->st>>>(h->camprep.p, h->tile_cam.p, h->tile_start.p,
                                                          h->tile_cnt.p, h->frame.p, h->xr.p, h->yr.p,
                                                          h->obs_u.p, h->obs_v.p, h->desc.opt_calib,
-                                                         h->desc.undist_points, tmp.p, tmp.p + h->N, tmp.p + 2 * h->N);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaMemcpyAsync(t, tmp.p, h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(u, tmp.p + h->N, h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(v, tmp.p + 2 * h->N, h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
-    tmp.release();
-    if (e != cudaSuccess) return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e));
+                                                         h->desc.undist_points, h->row_off.p, h->scratch.p);
+    MV_CUDA(h, cudaGetLastError());
+    MV_CUDA(h, cudaMemcpyAsync(out, h->scratch.p, (size_t)3 * h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    MV_CUDA(h, cudaStreamSynchronize(h->st));
     return MVUS_OK;
 }
 

@@ -39,13 +39,12 @@ class FlatProblem:
         self.Pc = 3 + self.C
         self.P = self.Pc + 12
 
-        dets = [np.asarray(scene.detections[i], dtype=np.float64) for i in self.seq]
-        self.N_cam = np.array([d.shape[1] for d in dets], dtype=np.int64)
+        # per-camera 3 x N_i arrays with contiguous rows (no copy when the Scene already holds
+        # C-contiguous float64 arrays; np.loadtxt(...).T in the reference gives strided rows -> copy)
+        self.dets = [np.ascontiguousarray(scene.detections[i], dtype=np.float64) for i in self.seq]
+        self.N_cam = np.array([d.shape[1] for d in self.dets], dtype=np.int64)
         self.cam_ptr = np.concatenate(([0], np.cumsum(self.N_cam))).astype(np.int64)
         self.N = int(self.cam_ptr[-1])
-        self.frame = np.ascontiguousarray(np.concatenate([d[0] for d in dets])) if self.N else np.zeros(0)
-        self.x_raw = np.ascontiguousarray(np.concatenate([d[1] for d in dets])) if self.N else np.zeros(0)
-        self.y_raw = np.ascontiguousarray(np.concatenate([d[2] for d in dets])) if self.N else np.zeros(0)
         cams = [scene.cameras[i] for i in self.seq]
         self.height = np.array([c.resolution[1] for c in cams], dtype=np.float64)
         self.calib = np.array([[c.K[0, 0], c.K[1, 1], c.K[0, 2], c.K[1, 2]] +
@@ -65,6 +64,21 @@ class FlatProblem:
         self.n_other = self.nc * self.Pc
         self.n = self.n_other + 3 * self.n_ctrl
         self.x0 = self.pack(scene)
+
+    def _cat(self, row):
+        return np.ascontiguousarray(np.concatenate([d[row] for d in self.dets])) if self.N else np.zeros(0)
+
+    @property
+    def frame(self):
+        return self._cat(0)
+
+    @property
+    def x_raw(self):
+        return self._cat(1)
+
+    @property
+    def y_raw(self):
+        return self._cat(2)
 
     # -- common.py:616-650 -------------------------------------------------------------
     def pack(self, scene):
