@@ -254,7 +254,7 @@ def main():
             'roofline': roof, 'phases': phases, 'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'seconds': dt_e2e, 'steps': e2e_steps},
-            'gpu_launches': int(st.launches), 'final_cost': st.cost, 'cost0': st.cost0,
+            'gpu_launches': int(st.launches), 'linear_solves': int(st.lm_iterations), 'final_cost': st.cost, 'cost0': st.cost0,
             'workload_gen_s': t_gen}
     if world == 1 and not a.no_cpu_baseline:
         _, info, _, _ = cpu_reference_run(a, 9, 1)

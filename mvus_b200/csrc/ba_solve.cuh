@@ -416,62 +416,95 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* _
     if (tid == 0 && s_bad) atomicExch(fail_flag, 1);
 }
 
-// S~ = sum over rows of W~^T W~ (lower-triangle tiles), FP64 SYRK with split-K + atomics.
-// grid = (tile pairs ti >= tj, K slabs), 256 threads, 128x128 output tile, 8x8 register
-// micro-tile per thread with a STRIDED column mapping (thread (tx,ty) owns rows ty+16*i and
-// columns tx+16*j): every shared-memory read of the B panel is unit-stride across the warp and
-// every read of the A panel is a broadcast -> no bank conflicts (the first version, 4x4
-// contiguous micro-tiles, measured 86 M conflicts and 4.4 TFLOP/s, profiles/r1_notes.md).
-constexpr int SY_T = 128, SY_K = 16;
-__global__ void __launch_bounds__(256)
+// S~ = sum over rows of W~^T W~ (lower-triangle tiles): the Schur complement's dense FP64
+// GEMM (ncP^2 * 3 n_ctrl flops = 200 GFLOP at config 4).  FP64 MMA (mma.sync m8n8k4 f64 -- the
+// only FP64 tensor instruction; tcgen05 has no f64 kind), 128x128 output tile per CTA, 16 warps
+// each owning a 32x32 warp tile = 4x4 fragments (32 accumulator doubles per thread), K chunks
+// of 16 rows staged in shared memory with a +4 padded leading dimension (fragment loads are
+// bank-conflict free: lane -> (k = lane&3, m = lane>>2) -> 4*k + m distinct 8-byte banks per
+// half warp), next chunk prefetched into registers while the current one is multiplied.
+// Split-K over row slabs, partial tiles reduced with FP64 RED.
+// History (profiles/r1_notes.md): v1 4x4 scalar micro-tiles 4.4 TFLOP/s (86 M bank conflicts),
+// v2 8x8 scalar micro-tiles 6.2 TFLOP/s (164 registers, 1 CTA/SM).
+constexpr int SY_T = 128, SY_K = 16, SY_LD = SY_T + 4;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(512)
 syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int slab, double* __restrict__ Sfull) {
-    __shared__ double As[SY_K][SY_T], Bs[SY_K][SY_T];
+    __shared__ double As[SY_K][SY_LD], Bs[SY_K][SY_LD];
     int p = blockIdx.x, ti = 0;
     while (p >= ti + 1) { p -= ti + 1; ++ti; }
     const int tj = p;
+    const bool diag = (ti == tj);
     const int64_t r0 = (int64_t)blockIdx.y * slab;
     const int64_t r1 = r0 + slab < R ? r0 + slab : R;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double acc[8][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wy = warp >> 2, wx = warp & 3;               // 4 x 4 warps of 32 x 32
+    const int fk = lane & 3, fm = lane >> 2;               // fragment coordinates
+    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
-    const bool diag = (ti == tj);
-    for (int64_t rr = r0; rr < r1; rr += SY_K) {
-        // 16 rows x 128 columns per panel: thread loads 8 elements of each panel
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    // each thread stages 4 elements of each panel per chunk: idx = tid + 512*k -> (row, col)
+    double pa[4], pb[4];
+    auto gload = [&](int64_t rr) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int idx = threadIdx.x + k * 256;
+        for (int k = 0; k < 4; ++k) {
+            const int idx = tid + k * 512;
             const int kk = idx >> 7, cc = idx & 127;
             const int64_t row = rr + kk;
             const int ca = ti * SY_T + cc, cb = tj * SY_T + cc;
             const bool inr = row < r1;
-            As[kk][cc] = (inr && ca < ldw) ? Ww[row * ldw + ca] : 0.0;
-            if (!diag) Bs[kk][cc] = (inr && cb < ldw) ? Ww[row * ldw + cb] : 0.0;
+            pa[k] = (inr && ca < ldw) ? __ldg(Ww + row * ldw + ca) : 0.0;
+            pb[k] = (!diag && inr && cb < ldw) ? __ldg(Ww + row * ldw + cb) : 0.0;
         }
+    };
+    auto sstore = [&]() {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int idx = tid + k * 512;
+            const int kk = idx >> 7, cc = idx & 127;
+            As[kk][cc] = pa[k];
+            if (!diag) Bs[kk][cc] = pb[k];
+        }
+    };
+    gload(r0);
+    for (int64_t rr = r0; rr < r1; rr += SY_K) {
+        sstore();
         __syncthreads();
-        const double (*Bp)[SY_T] = diag ? As : Bs;
-#pragma unroll 4
-        for (int kk = 0; kk < SY_K; ++kk) {
-            double a[8], b[8];
+        if (rr + SY_K < r1) gload(rr + SY_K);
+        const double (*Bp)[SY_LD] = diag ? As : Bs;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { a[i] = As[kk][ty + 16 * i]; b[i] = Bp[kk][tx + 16 * i]; }
+        for (int ks = 0; ks < SY_K; ks += 4) {
+            double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i) {
+                a[i] = As[ks + fk][wy * 32 + i * 8 + fm];
+                b[i] = Bp[ks + fk][wx * 32 + i * 8 + fm];
+            }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int row = ti * SY_T + ty + 16 * i, col = tj * SY_T + tx + 16 * j;
-            if (row < ldw && col <= row && acc[i][j] != 0.0)
-                atomicAdd(Sfull + (int64_t)row * ldw + col, acc[i][j]);
-        }
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int row = ti * SY_T + wy * 32 + i * 8 + fm;
+                const int col = tj * SY_T + wx * 32 + j * 8 + fk * 2 + e;
+                const double v = acc[i][j][e];
+                if (row < ldw && col <= row && v != 0.0) atomicAdd(Sfull + (int64_t)row * ldw + col, v);
+            }
 }
 
 // S = blockdiag(A) + lam * diag - S~ (lower triangle), rhs = bc - S~[ncP][:]
@@ -848,7 +881,7 @@ inline int accumulate(mvus_ba_ctx* h) {
         }
         h->launches++;
     }
-    if (h->M > 0) {
+    if (h->M > 0 && (h->world <= 1 || h->rank == 0)) {      // parameter-only rows: counted once
         accumulate_motion_kernel<<<(int)((h->M + 127) / 128), 128, 0, h->st>>>(
             h->r.p + 2 * h->N, h->mbase.p, h->mJ.p, h->M, h->bw, h->ldw, h->D.p, h->E.p, h->W.p);
         h->launches++;
@@ -858,6 +891,8 @@ inline int accumulate(mvus_ba_ctx* h) {
 }
 
 int allreduce_normal_equations(mvus_ba_ctx* h);   // ba_nccl.cuh
+int nccl_bcast0(mvus_ba_ctx* h, double* buf, size_t count);
+int nccl_max_flag(mvus_ba_ctx* h, int* flag);
 
 inline int compute_diag(mvus_ba_ctx* h) {
     const int64_t nbq = h->nb * h->q;
@@ -919,7 +954,7 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
     int64_t nslab = std::max<int64_t>(1, (4 * h->sm_count + npairs - 1) / npairs);
     int slab = (int)std::max<int64_t>(256, ((nbq + nslab - 1) / nslab + SY_K - 1) / SY_K * SY_K);
     dim3 g(npairs, (unsigned)((nbq + slab - 1) / slab));
-    syrk_kernel<<<g, 256, 0, h->st>>>(h->Ww.p, nbq, ldw, slab, h->Sd.p);
+    syrk_kernel<<<g, 512, 0, h->st>>>(h->Ww.p, nbq, ldw, slab, h->Sd.p);
     form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
         h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->Sd.p, rhs);
     h->launches += 2;
@@ -936,6 +971,12 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
         h->launches++;
     }
     MV_CUDA(h, cudaGetLastError());
+    if (h->world > 1) {
+        int e = nccl_max_flag(h, fail_flag);
+        if (!e) e = nccl_bcast0(h, h->dlt_c.p, (size_t)h->ncP);
+        if (!e) e = nccl_bcast0(h, h->dlt_s.p, (size_t)nbq);
+        if (e) return e;
+    }
     int f = 0;
     MV_CUDA(h, cudaMemcpyAsync(&f, fail_flag, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     MV_CUDA(h, cudaStreamSynchronize(h->st));

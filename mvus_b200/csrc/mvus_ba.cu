@@ -270,6 +270,8 @@ int mvus::evaluate(mvus_ba_ctx* h, const double* xd, bool want_j) {
                                                         h->tau.p, h->tau_spl.p, h->tau_flag.p, h->M,
                                                         h->r.p + 2 * h->N, nullptr, nullptr,
                                                         h->partial.p + np, h->flag.p);
+        if (h->world > 1 && h->rank != 0)     // motion rows count once in the all-reduced cost
+            MV_CUDA(h, cudaMemsetAsync(h->partial.p + np, 0, (size_t)gb * sizeof(double), h->st));
         np += gb;
         h->launches++;
     }
@@ -436,7 +438,7 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
     st.nfev = 1; st.njev = 1;
     // Levenberg-Marquardt with trust-region control of the step length (More, as in MINPACK's
     // lmpar, and the radius update of scipy/optimize/_lsq/trf.py:526-541): lambda is chosen so
-    // that the scaled step norm |delta|_D is within 25% of the radius Delta; a poor step shrinks
+    // that the scaled step norm |delta|_D is within [0.5, 1.5] of the radius Delta; a poor step shrinks
     // Delta to |delta|_D / 4, a very good one at the boundary doubles it.  Re-solving for a new
     // lambda costs linear solves but no residual evaluations (nfev is what max_iter caps).
     const double lam_min = 1e-10;
@@ -471,8 +473,8 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
         // bracket / secant search on lambda (log scale) for |delta|_D ~ Delta
         double lo_l = -1, lo_n = 0, hi_l = -1, hi_n = 0;
         for (int its = 0; its < 10; ++its) {
-            if (!ok || nrm > 1.25 * Delta) { lo_l = lam; lo_n = nrm; }
-            else if (nrm < 0.75 * Delta && lam > lam_min) { hi_l = lam; hi_n = nrm; }
+            if (!ok || nrm > 1.5 * Delta) { lo_l = lam; lo_n = nrm; }
+            else if (nrm < 0.5 * Delta && lam > lam_min) { hi_l = lam; hi_n = nrm; }
             else break;
             if (lo_l > 0 && hi_l > 0 && lo_n < 1e299) {
                 const double a = std::log(lo_l), b = std::log(hi_l);
