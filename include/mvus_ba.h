@@ -149,6 +149,14 @@ int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, double* r_o
  * array the reference stores in Scene.detections_global[i] (np.vstack, common.py:127). */
 int mvus_ba_detections_global(mvus_ba_handle h, const double* x, double* out);
 
+/* Bookkeeping output of Scene.all_detect_to_traj (common.py:887-944) at parameters x:
+ * `global_traj` = every detection of the optimised cameras whose global time stamp lies inside
+ * a spline interval (closed ends, common.py:292), sorted by time stamp.  out: 7 x n_out
+ * row-major (rows: running index, camera id taken from cam_ids[nc], frame id, time stamp,
+ * X, Y, Z of the spline at that time); the buffer must hold 7*N doubles. */
+int mvus_ba_global_traj(mvus_ba_handle h, const double* x, const int32_t* cam_ids, int64_t* n_out,
+                        double* out);
+
 /* Diagnostics used by the parity tests: the normal equations K2 assembles at x.
  *   A    [nc*Pc*Pc]  camera diagonal blocks (Pc = 3 + C), row-major per camera
  *   g    [n]         J^T r in the reference's x layout

@@ -38,7 +38,7 @@ class BAStats(ctypes.Structure):
 EXPORTS = ['mvus_ba_version', 'mvus_ba_create', 'mvus_ba_destroy', 'mvus_ba_last_error',
            'mvus_ba_set_detections', 'mvus_ba_set_detections_rows', 'mvus_ba_set_splines', 'mvus_ba_dims', 'mvus_ba_residual',
            'mvus_ba_residual_jacobian', 'mvus_ba_solve', 'mvus_ba_detections_global',
-           'mvus_ba_normal_equations', 'mvus_ba_nccl_unique_id', 'mvus_ba_comm_init',
+           'mvus_ba_normal_equations', 'mvus_ba_global_traj', 'mvus_ba_nccl_unique_id', 'mvus_ba_comm_init',
            'mvus_ba_time_resjac', 'mvus_ba_time_accumulate']
 
 _lib = None
@@ -73,6 +73,7 @@ def load():
     lib.mvus_ba_solve.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, ctypes.POINTER(BAStats)]
     lib.mvus_ba_detections_global.argtypes = [ctypes.c_void_p, _dp, _dp]
     lib.mvus_ba_normal_equations.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp, _ip, _dp, _dp]
+    lib.mvus_ba_global_traj.argtypes = [ctypes.c_void_p, _dp, _ip, _lp, _dp]
     lib.mvus_ba_nccl_unique_id.argtypes = [ctypes.c_char_p]
     lib.mvus_ba_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p]
     lib.mvus_ba_time_resjac.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int32, _dp]
@@ -175,6 +176,14 @@ class Handle:
         # zero-copy 3 x N_i views, one per camera: the arrays Scene.detections_global holds
         cp = self.fp.cam_ptr
         return [out[3 * cp[k]:3 * cp[k + 1]].reshape(3, -1) for k in range(self.fp.nc)]
+
+    def global_traj(self, x, cam_ids):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        ids = np.ascontiguousarray(cam_ids, dtype=np.int32)
+        out = np.empty(7 * max(self.N, 1))
+        n = ctypes.c_int64()
+        self._check(self.lib.mvus_ba_global_traj(self.h, _d(x), _i(ids), ctypes.byref(n), _d(out)))
+        return out[:7 * n.value].reshape(7, n.value)
 
     def normal_equations(self, x, want_dense=True):
         fp = self.fp

@@ -179,20 +179,22 @@ def spline_to_traj(scene, sampling_rate=1, t=None):
     return scene.traj
 
 
-def _all_detect_to_traj(scene, cams):
-    """Bookkeeping of Scene.all_detect_to_traj (common.py:887-944) from refreshed
-    detections_global: global_time_stamps_all, frame_id_all, global_detections, global_traj."""
-    ts = np.concatenate([scene.detections_global[i][0] for i in cams])
-    fid = np.concatenate([np.asarray(scene.detections[i][0], dtype=np.float64) for i in cams])
-    cid = np.concatenate([np.ones(scene.detections[i].shape[1]) * i for i in cams])
-    scene.frame_id_all = fid
-    scene.global_time_stamps_all = ts
-    traj = spline_to_traj(scene, t=np.sort(ts))
-    scene.global_detections = np.vstack((cid, fid, ts))
-    tmp = scene.global_detections[:, np.argsort(scene.global_detections[2, :])]
-    keep = np.isin(tmp[2], traj[0])
-    tmp = np.vstack((tmp[:, keep], traj[1:]))
-    scene.global_traj = np.vstack((np.arange(tmp.shape[1]), tmp))
+def _all_detect_to_traj(scene, fp, hd, x):
+    """Bookkeeping of Scene.all_detect_to_traj (common.py:887-944): global_time_stamps_all,
+    frame_id_all, global_detections from the refreshed detections_global; global_traj (sorted,
+    in-interval detections with their spline positions) from the device (mvus_ba_global_traj)."""
+    cams = fp.seq
+    N = fp.N
+    gd = np.empty((3, N))
+    for k, i in enumerate(cams):
+        a, b = fp.cam_ptr[k], fp.cam_ptr[k + 1]
+        gd[0, a:b] = i
+        gd[1, a:b] = fp.dets[k][0]
+        gd[2, a:b] = scene.detections_global[i][0]
+    scene.global_detections = gd
+    scene.frame_id_all = gd[1].copy()
+    scene.global_time_stamps_all = gd[2].copy()
+    scene.global_traj = hd.global_traj(x, cams)
 
 
 def bundle_adjust(scene, numCam, max_iter=10, rs=False, motion_prior=False, motion_reg=False,
@@ -237,15 +239,12 @@ def bundle_adjust(scene, numCam, max_iter=10, rs=False, motion_prior=False, moti
         x, r, st = hd.solve(fp.x0)
         fp.unpack_into(scene, x)            # common.py:672-692
         refresh(hd, x, False)               # common.py:695
+        if motion_reg and bookkeeping:
+            _all_detect_to_traj(scene, fp, hd, x)
+            spline_to_traj(scene)           # common.py:379 leaves traj = unit-step samples
     finally:
         if not return_handle:
             hd.close()
-
-    if motion_reg and bookkeeping:
-        spline_to_traj(scene)                      # common.py:379 leaves traj = unit-step samples
-        unit_traj = scene.traj
-        _all_detect_to_traj(scene, fp.seq)
-        scene.traj = unit_traj
 
     res = OptimizeResult(x=x, cost=st.cost, fun=r, jac=None, grad=None, optimality=st.optimality,
                          active_mask=np.zeros(fp.n, dtype=int), nfev=st.nfev, njev=st.njev,

@@ -10,6 +10,7 @@
 #include "ba_kernels.cuh"
 #include "ba_solve.cuh"
 #include "ba_nccl.cuh"
+#include "ba_bookkeeping.cuh"
 
 using namespace mvus;
 
@@ -646,5 +647,64 @@ extern "C" int mvus_ba_time_accumulate(mvus_ba_handle h, int32_t reps, double* m
     float ms = 0.f;
     MV_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
     *ms_mean = (double)ms / reps;
+    return MVUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" int mvus_ba_global_traj(mvus_ba_handle h, const double* x, const int32_t* cam_ids,
+                                   int64_t* n_out, double* out) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!x || !cam_ids || !n_out || !out) return fail(h, MVUS_ERR_ARG, "null argument");
+    *n_out = 0;
+    const int64_t N = h->N;
+    if (N == 0) return MVUS_OK;
+    MV_CUDA(h, cudaMemcpyAsync(h->x.p, x, h->n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    cam_prep_kernel<<<(h->nc + 63) / 64, 64, 0, h->st>>>(h->x.p, h->nc, h->C, h->desc.opt_calib, h->calib.p,
+                                                         h->height.p, h->camprep.p);
+    DevBuf<double> ts, ts_s;
+    DevBuf<int> idx, idx_s, flag, pos, cams;
+    DevBuf<unsigned char> tmp;
+    cudaError_t e = ts.alloc(N);
+    if (e == cudaSuccess) e = ts_s.alloc(N);
+    if (e == cudaSuccess) e = idx.alloc(N);
+    if (e == cudaSuccess) e = idx_s.alloc(N);
+    if (e == cudaSuccess) e = flag.alloc(N);
+    if (e == cudaSuccess) e = pos.alloc(N);
+    if (e == cudaSuccess) e = upload(cams, cam_ids, (size_t)h->nc, h->st);
+    size_t tb1 = 0, tb2 = 0;
+    if (e == cudaSuccess) e = cub::DeviceRadixSort::SortPairs(nullptr, tb1, ts.p, ts_s.p, idx.p, idx_s.p, (int)N, 0, 64, h->st);
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tb2, flag.p, pos.p, (int)N, h->st);
+    size_t tb = tb1 > tb2 ? tb1 : tb2;
+    if (e == cudaSuccess) e = tmp.alloc(tb);
+    auto cleanup = [&]() { ts.release(); ts_s.release(); idx.release(); idx_s.release(); flag.release(); pos.release(); cams.release(); tmp.release(); };
+    if (e != cudaSuccess) { cleanup(); return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e)); }
+    gt_times_kernel<<<h->n_tiles, TILE_DET, 0, h->st>>>(h->camprep.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p,
+                                                       h->frame.p, h->yr.p, ts.p, idx.p);
+    e = cub::DeviceRadixSort::SortPairs(tmp.p, tb, ts.p, ts_s.p, idx.p, idx_s.p, (int)N, 0, 64, h->st);
+    const int gb = (int)((N + 255) / 256);
+    if (e == cudaSuccess) {
+        gt_flag_kernel<<<gb, 256, 0, h->st>>>(h->sv, ts_s.p, N, flag.p);
+        e = cub::DeviceScan::ExclusiveSum(tmp.p, tb, flag.p, pos.p, (int)N, h->st);
+    }
+    int last_pos = 0, last_flag = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&last_pos, pos.p + (N - 1), sizeof(int), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&last_flag, flag.p + (N - 1), sizeof(int), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    if (e != cudaSuccess) { cleanup(); return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e)); }
+    const int64_t n = (int64_t)last_pos + last_flag;
+    *n_out = n;
+    if (n > 0) {
+        e = h->scratch.alloc((size_t)7 * n);
+        if (e == cudaSuccess) {
+            gt_gather_kernel<<<gb, 256, 0, h->st>>>(h->sv, h->x.p, ts_s.p, idx_s.p, flag.p, pos.p, N, n, h->row_off.p,
+                                                   h->nc, cams.p, h->frame.p, h->scratch.p);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, h->scratch.p, (size_t)7 * n * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    }
+    cleanup();
+    if (e != cudaSuccess) return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e));
     return MVUS_OK;
 }

@@ -101,3 +101,23 @@ def emul_resjac(fp, x):
                          mbase.ctypes.data_as(ip), D(mJ))
     assert rc == 0, rc
     return r, span, J, mbase, mJ
+
+
+def numpy_all_detect_to_traj(scene, cams):
+    """NumPy restatement of Scene.all_detect_to_traj (common.py:887-944) on a scene whose
+    detections_global is current; returns global_traj (7 x n)."""
+    from scipy import interpolate
+    ts = np.concatenate([scene.detections_global[i][0] for i in cams])
+    fid = np.concatenate([np.asarray(scene.detections[i][0], dtype=np.float64) for i in cams])
+    cid = np.concatenate([np.ones(scene.detections[i].shape[1]) * i for i in cams])
+    tck, interval = scene.spline['tck'], np.asarray(scene.spline['int'])
+    tsort = np.sort(ts)
+    traj = np.empty([4, 0])
+    for i in range(interval.shape[1]):
+        part = tsort[np.logical_and(tsort >= interval[0, i], tsort <= interval[1, i])]
+        traj = np.hstack((traj, np.vstack((part, np.asarray(interpolate.splev(part, tck[i]))))))
+    gd = np.vstack((cid, fid, ts))
+    tmp = gd[:, np.argsort(gd[2, :], kind='stable')]
+    keep = np.isin(tmp[2], traj[0])
+    tmp = np.vstack((tmp[:, keep], traj[1:]))
+    return np.vstack((np.arange(tmp.shape[1]), tmp))

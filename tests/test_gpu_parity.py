@@ -167,5 +167,10 @@ def test_scene_ba_postconditions(built_lib):
         assert np.abs(fl.detections_global[i][1] - c['uo']).max() <= 1e-9 * 2000
         assert (det_before[i] == fl.detections[i]).all()
     assert fl.traj.shape[0] == 4 and fl.global_traj.shape[0] == 7
+    gt = helpers.numpy_all_detect_to_traj(fl, list(range(fl.numCam)))
+    assert gt.shape == fl.global_traj.shape
+    assert (gt[:3] == fl.global_traj[:3]).all()                     # index, camera, frame (same order)
+    assert np.abs(gt[3:] - fl.global_traj[3:]).max() <= 1e-9 * max(1.0, np.abs(gt[3:]).max())
+    assert fl.global_detections.shape == (3, sum(d.shape[1] for d in fl.detections))
     import pickle
     pickle.dumps(fl)
