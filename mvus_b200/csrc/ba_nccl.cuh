@@ -49,9 +49,12 @@ struct NcclApi {
 inline NcclApi& nccl_api() { static NcclApi a; return a; }
 constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;   // ncclDouble, ncclSum (stable ABI values)
 
-inline void nccl_destroy(mvus_ba_ctx* h) {
-    if (h->nccl_comm) { nccl_api().CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
-}
+// One communicator per process and unique id (an id can initialise only one communicator);
+// handles share it and it lives until the process exits.
+struct CommCache { std::string uid; void* comm = nullptr; int world = 0, rank = 0; };
+inline CommCache& comm_cache() { static CommCache c; return c; }
+
+inline void nccl_destroy(mvus_ba_ctx* h) { h->nccl_comm = nullptr; }
 
 inline int nccl_sum(mvus_ba_ctx* h, double* buf, size_t count) {
     if (h->world <= 1 || count == 0) return MVUS_OK;
@@ -111,10 +114,18 @@ extern "C" int mvus_ba_comm_init(mvus_ba_handle h, int32_t world_size, int32_t r
     std::string err;
     if (!mvus::nccl_api().load(err)) return mvus::fail(h, MVUS_ERR_NCCL, err);
     MV_CUDA(h, cudaSetDevice(h->desc.device));
-    mvus::nccl_uid_t uid;
-    memcpy(uid.internal, id, 128);
-    const int rc = mvus::nccl_api().CommInitRank(&h->nccl_comm, world_size, uid, rank);
-    if (rc != 0) return mvus::fail(h, MVUS_ERR_NCCL, "ncclCommInitRank failed");
+    mvus::CommCache& cc = mvus::comm_cache();
+    const std::string key(id, 128);
+    if (!(cc.comm && cc.uid == key && cc.world == world_size && cc.rank == rank)) {
+        mvus::nccl_uid_t uid;
+        memcpy(uid.internal, id, 128);
+        void* comm = nullptr;
+        const int rc = mvus::nccl_api().CommInitRank(&comm, world_size, uid, rank);
+        if (rc != 0) return mvus::fail(h, MVUS_ERR_NCCL, std::string("ncclCommInitRank failed: ") +
+                                       (mvus::nccl_api().GetErrorString ? mvus::nccl_api().GetErrorString(rc) : ""));
+        cc.uid = key; cc.comm = comm; cc.world = world_size; cc.rank = rank;
+    }
+    h->nccl_comm = cc.comm;
     h->world = world_size;
     h->rank = rank;
     return MVUS_OK;

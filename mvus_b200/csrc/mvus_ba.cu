@@ -444,6 +444,8 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
     // lambda costs linear solves but no residual evaluations (nfev is what max_iter caps).
     const double lam_min = 1e-10;
     double lam = 1e-4, Delta = -1.0;
+    double pexp = 2.0 / 3.0;          // running estimate of p in |delta|_D ~ lambda^-p
+    double last_l = -1.0, last_n = 0.0;
     int status = 0;
     bool r_is_current = true, need_accum = true;
     double sc[5] = {0, 0, 0, 0, 0};
@@ -468,9 +470,12 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
         }
         int ok = 0;
         double nrm = 0.0;
+        if (Delta > 0.0 && last_l > 0.0 && last_n > 0.0 && last_n < 1e299)   // aim the first solve at Delta
+            lam = std::min(std::max(last_l * std::pow(last_n / Delta, 1.0 / pexp), lam_min), 1e30);
         rc = solve_norm(lam, &ok, &nrm);
         if (rc) return rc;
         if (ok && Delta < 0.0) Delta = nrm;
+        double prev_l = ok ? lam : -1.0, prev_n = nrm;
         // bracket / secant search on lambda (log scale) for |delta|_D ~ Delta
         double lo_l = -1, lo_n = 0, hi_l = -1, hi_n = 0;
         for (int its = 0; its < 10; ++its) {
@@ -486,17 +491,23 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
             } else if (lo_l > 0 && hi_l > 0) {
                 lam = std::sqrt(lo_l * hi_l);
             } else if (lo_l > 0) {
-                const double f = ok ? std::pow(std::max(nrm / Delta, 2.0), 1.5) : 10.0;
-                lam = std::max(lam * f, lam * 4.0);
+                const double f = ok ? std::pow(nrm / Delta, 1.0 / pexp) : 10.0;
+                lam = std::max(lam * f, lam * 2.0);
                 if (lam > 1e30) break;
             } else {
-                lam = std::max(lam * std::pow(std::min(nrm / Delta, 0.5), 1.5), lam_min);
+                lam = std::max(std::min(lam * std::pow(nrm / Delta, 1.0 / pexp), lam * 0.5), lam_min);
             }
             rc = solve_norm(lam, &ok, &nrm);
             if (rc) return rc;
             if (ok && Delta < 0.0) Delta = nrm;
+            if (ok && prev_l > 0.0 && prev_n < 1e299 && lam != prev_l && nrm > 0.0 && prev_n > 0.0) {
+                const double pe = -std::log(nrm / prev_n) / std::log(lam / prev_l);
+                if (std::isfinite(pe)) pexp = std::min(std::max(pe, 0.15), 1.0);
+            }
+            if (ok) { prev_l = lam; prev_n = nrm; }
         }
         if (!ok) { status = -1; break; }
+        last_l = lam; last_n = nrm;
         st.optimality = __longlong_as_double_host(sc[4]);
         if (r_is_current && st.optimality < gtol) { status = 1; break; }
         const double pred = 0.5 * (lam * sc[0] + sc[1]);
@@ -521,7 +532,6 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
         const bool x_small = step_norm < xtol * (xtol + x_norm);
         if (std::isfinite(Fn) && actual > 0.0) {
             std::swap(h->x.p, h->x_trial.p);
-            if (ratio > 0.75) lam = std::max(lam / 3.0, lam_min);
             const bool f_small = actual < ftol * Fn && ratio > 0.25;
             F = Fn;
             if (f_small && x_small) status = 4;
