@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
+#include <cstdio>
 #include <string>
 #include <vector>
 
@@ -443,6 +445,7 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
     // Delta to |delta|_D / 4, a very good one at the boundary doubles it.  Re-solving for a new
     // lambda costs linear solves but no residual evaluations (nfev is what max_iter caps).
     const double lam_min = 1e-10;
+    const bool verbose = getenv("MVUS_BA_VERBOSE") != nullptr;
     double lam = 1e-4, Delta = -1.0;
     double pexp = 2.0 / 3.0;          // running estimate of p in |delta|_D ~ lambda^-p
     double last_l = -1.0, last_n = 0.0;
@@ -456,6 +459,7 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
         t.stop();
         st.lm_iterations++;
         *nrm = *ok ? std::sqrt(sc[0]) : 1e300;
+        if (verbose) fprintf(stderr, "[mvus_ba]   solve lam %.3e ok %d |d|_D %.4e Delta %.4e p %.3f\n", l, *ok, *nrm, Delta, pexp);
         return e;
     };
     while (st.nfev < max_nfev && status == 0) {
@@ -483,11 +487,12 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
             else if (nrm < 0.5 * Delta && lam > lam_min) { hi_l = lam; hi_n = nrm; }
             else break;
             if (lo_l > 0 && hi_l > 0 && lo_n < 1e299) {
+                // bracketed: |delta|_D(lambda) is monotone but has plateaus and cliffs, so interpolate
+                // in log-log and stay within the middle half of the bracket (bisection-like progress)
                 const double a = std::log(lo_l), b = std::log(hi_l);
-                const double fa = 1.0 / lo_n - 1.0 / Delta, fb = 1.0 / hi_n - 1.0 / Delta;
-                double t = a - fa * (b - a) / (fb - fa);
-                t = std::min(std::max(t, a + 0.1 * (b - a)), b - 0.1 * (b - a));
-                lam = std::exp(t);
+                double w = (std::log(lo_n) - std::log(Delta)) / (std::log(lo_n) - std::log(hi_n));
+                w = std::min(std::max(w, 0.25), 0.75);
+                lam = std::exp(a + w * (b - a));
             } else if (lo_l > 0 && hi_l > 0) {
                 lam = std::sqrt(lo_l * hi_l);
             } else if (lo_l > 0) {
@@ -527,6 +532,8 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
         r_is_current = false;
         const double actual = F - Fn;
         const double ratio = (pred > 0.0 && std::isfinite(Fn)) ? actual / pred : -1.0;
+        if (verbose) fprintf(stderr, "[mvus_ba] nfev %d F %.8e Fn %.8e ratio %.3f lam %.3e |d|_D %.3e Delta %.3e |g|inf %.3e\n",
+                             st.nfev, F, Fn, ratio, lam, nrm, Delta, st.optimality);
         if (ratio < 0.25) Delta = 0.25 * nrm;
         else if (ratio > 0.75 && nrm > 0.7 * Delta) Delta *= 2.0;
         const bool x_small = step_norm < xtol * (xtol + x_norm);
