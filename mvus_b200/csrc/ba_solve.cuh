@@ -298,8 +298,12 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* _
     __shared__ double zl_p[Q * Q], zr_p[Q * Q];   // ZL, ZR of the RIGHT eliminated neighbour (j + sp)
     __shared__ double Dj[Q * Q], El[Q * Q], Er[Q * Q];
     __shared__ int s_bad;
+    // root: 0 = regular level, 1 = final pass on block 0, 2 = update-only pass (sharded solve:
+    // apply the pending updates of the last local level and leave the bridged coupling in Ew[j])
+    const bool upd_only = (root == 2);
+    if (upd_only) root = 0;
     const int64_t j = root ? 0 : (int64_t)blockIdx.x * s;
-    const bool elim = root || (((j / s) & 1) == 1);
+    const bool elim = !upd_only && (root || (((j / s) & 1) == 1));
     const int tid = threadIdx.x, nt = blockDim.x;
     const int qq = q * q;
     const bool has_m = sp > 0 && j - sp >= 0 && (((j - sp) / sp) & 1);
@@ -378,6 +382,8 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* _
     }
 #pragma unroll 1
     for (int i = tid; i < qq; i += nt) Dw[j * qq + i] = Dj[i];
+    if (upd_only && sp > 0)
+        for (int i = tid; i < qq; i += nt) Ew[j * qq + i] = (j + s < nb) ? Er[i] : 0.0;
     // W~ columns: pending update, then forward substitution if eliminated
     const double* Wm = Ww + (j - sp) * (int64_t)q * ldw;
     const double* Wp = Ww + (j + sp) * (int64_t)q * ldw;
@@ -837,21 +843,34 @@ inline int solver_alloc(mvus_ba_ctx* h) {
     h->bw = std::max(3, spread - 1);
     h->q = 3 * h->bw;
     h->nb = (h->n_ctrl + h->bw - 1) / h->bw;
+    h->Bc = 1;
+    if (h->world > 1) {
+        // chunk size for the sharded solve: power of two, ~8 chunks per rank, >= 1
+        while (h->Bc * 2 * 8 * h->world <= h->nb) h->Bc *= 2;
+        h->nb = (h->nb + h->Bc - 1) / h->Bc * h->Bc;       // padded with decoupled identity blocks
+    }
     h->ncP = h->nc * h->Pc;
     h->ldw = h->ncP + 1;
     if (h->ncP > 1152) return fail(h, MVUS_ERR_UNSUPPORTED, "more than 1152 camera unknowns");
     const size_t qq = (size_t)h->q * h->q;
     MV_CUDA(h, h->A.alloc((size_t)h->nc * h->Pc * h->Pc + h->ncP));      // A then bc
-    MV_CUDA(h, h->D.alloc(h->nb * qq));
-    MV_CUDA(h, h->E.alloc(h->nb * qq));
-    MV_CUDA(h, h->W.alloc((size_t)h->nb * h->q * h->ldw));
-    MV_CUDA(h, h->Dw.alloc(h->nb * qq));
-    MV_CUDA(h, h->Ew.alloc(h->nb * qq));
-    MV_CUDA(h, h->Ww.alloc((size_t)h->nb * h->q * h->ldw));
-    MV_CUDA(h, h->ZL.alloc(h->nb * qq));
+    const size_t nba = (size_t)h->nb + 1;                      // +1: ghost block of the sharded solve
+    MV_CUDA(h, h->D.alloc(nba * qq));
+    MV_CUDA(h, h->E.alloc(nba * qq));
+    MV_CUDA(h, h->W.alloc(nba * h->q * h->ldw));
+    MV_CUDA(h, h->Dw.alloc(nba * qq));
+    MV_CUDA(h, h->Ew.alloc(nba * qq));
+    MV_CUDA(h, h->Ww.alloc(nba * h->q * h->ldw));
+    MV_CUDA(h, h->ZL.alloc(nba * qq));
+    if (h->world > 1) {
+        const size_t nch = (size_t)(h->nb / h->Bc);
+        MV_CUDA(h, h->Dt.alloc(nch * (2 * qq + (size_t)h->q * h->ldw)));
+        MV_CUDA(h, h->ZLt.alloc(nch * qq));
+        MV_CUDA(h, h->dst.alloc(nch * h->q));
+    }
     MV_CUDA(h, h->Sd.alloc((size_t)h->ldw * h->ldw + h->ldw));           // S~ then rhs
     MV_CUDA(h, h->dlt_c.alloc(h->ncP));
-    MV_CUDA(h, h->dlt_s.alloc((size_t)h->nb * h->q));
+    MV_CUDA(h, h->dlt_s.alloc(((size_t)h->nb + 1) * h->q));
     MV_CUDA(h, h->diag_c.alloc(h->ncP));
     MV_CUDA(h, h->diag_s.alloc((size_t)h->nb * h->q));
     MV_CUDA(h, h->gvec.alloc(h->n));
@@ -893,6 +912,7 @@ inline int accumulate(mvus_ba_ctx* h) {
 int allreduce_normal_equations(mvus_ba_ctx* h);   // ba_nccl.cuh
 int nccl_bcast0(mvus_ba_ctx* h, double* buf, size_t count);
 int nccl_max_flag(mvus_ba_ctx* h, int* flag);
+int nccl_sum(mvus_ba_ctx* h, double* buf, size_t count);
 
 inline int compute_diag(mvus_ba_ctx* h) {
     const int64_t nbq = h->nb * h->q;
@@ -911,8 +931,12 @@ inline int compute_diag(mvus_ba_ctx* h) {
     return MVUS_OK;
 }
 
-inline void launch_level(mvus_ba_ctx* h, int grid, int64_t s, int64_t sp, int root, int* fail_flag) {
-#define MV_LVL(QQ) bcr_level_kernel<QQ><<<grid, 128, 0, h->st>>>(h->nb, h->ldw, s, sp, root, h->Dw.p, h->Ew.p, h->Ww.p, h->ZL.p, fail_flag)
+struct BcrView {          // a block-tridiagonal system (possibly a sub-range of the handle's arrays)
+    double* Dw; double* Ew; double* Ww; double* ZL; double* ds; int64_t nb;
+};
+
+inline void launch_level(mvus_ba_ctx* h, const BcrView& v, int grid, int64_t s, int64_t sp, int root, int* fail_flag) {
+#define MV_LVL(QQ) bcr_level_kernel<QQ><<<grid, 128, 0, h->st>>>(v.nb, h->ldw, s, sp, root, v.Dw, v.Ew, v.Ww, v.ZL, fail_flag)
     switch (h->q) {
         case 9: MV_LVL(9); break;
         case 12: MV_LVL(12); break;
@@ -923,60 +947,171 @@ inline void launch_level(mvus_ba_ctx* h, int grid, int64_t s, int64_t sp, int ro
     h->launches++;
 }
 
+// Elimination levels with strides 1, 2, .. < s_end (s_end = nb: all levels), optional root pass.
+inline std::vector<int64_t> bcr_eliminate(mvus_ba_ctx* h, const BcrView& v, int64_t s_end, bool with_root, int* fail_flag) {
+    std::vector<int64_t> levels;
+    for (int64_t s = 1; s < s_end && s < v.nb; s <<= 1) levels.push_back(s);
+    for (size_t lv = 0; lv < levels.size(); ++lv) {
+        const int64_t s = levels[lv], sp = lv ? levels[lv - 1] : 0;
+        launch_level(h, v, (int)((v.nb + s - 1) / s), s, sp, 0, fail_flag);
+    }
+    if (with_root)
+        launch_level(h, v, 1, levels.empty() ? 1 : levels.back() * 2, levels.empty() ? 0 : levels.back(), 1, fail_flag);
+    return levels;
+}
+
+inline void bcr_back(mvus_ba_ctx* h, const BcrView& v, const std::vector<int64_t>& levels, bool with_root) {
+    if (with_root) { bcr_back_kernel<<<1, 32, 0, h->st>>>(v.nb, h->q, 0, 1, v.Dw, v.Ew, v.ZL, v.ds); h->launches++; }
+    for (int lv = (int)levels.size() - 1; lv >= 0; --lv) {
+        const int64_t s = levels[lv];
+        const int64_t nel = (v.nb / s + 1) / 2;     // odd multiples of s below nb (kernel guards the rest)
+        if (nel <= 0) continue;
+        bcr_back_kernel<<<(int)nel, 32, 0, h->st>>>(v.nb, h->q, s, 0, v.Dw, v.Ew, v.ZL, v.ds);
+        h->launches++;
+    }
+}
+
+inline void launch_syrk(mvus_ba_ctx* h, const double* Wrows, int64_t R, double* Sfull) {
+    if (R <= 0) return;
+    const int ldw = h->ldw;
+    const int nts = (ldw + SY_T - 1) / SY_T, npairs = nts * (nts + 1) / 2;
+    // ~4 waves of CTAs over the SMs, slabs a multiple of the K chunk
+    int64_t nslab = std::max<int64_t>(1, (4 * h->sm_count + npairs - 1) / npairs);
+    int slab = (int)std::max<int64_t>(256, ((R + nslab - 1) / nslab + SY_K - 1) / SY_K * SY_K);
+    dim3 g(npairs, (unsigned)((R + slab - 1) / slab));
+    syrk_kernel<<<g, 512, 0, h->st>>>(Wrows, R, ldw, slab, Sfull);
+    h->launches++;
+}
+
+// copy the chunk-head blocks of this rank (and its ghost) into the compact top-level arrays
+__global__ void top_gather_kernel(const double* __restrict__ Dw, const double* __restrict__ Ew,
+                                  const double* __restrict__ Ww, int q, int ldw, int64_t Bc, int64_t c0,
+                                  int64_t c1, int64_t nchunks, double* __restrict__ Dt,
+                                  double* __restrict__ Et, double* __restrict__ Wt) {
+    const int64_t c = c0 + blockIdx.x;                 // blockIdx.x in [0, c1 - c0]: last one = ghost
+    if (c >= nchunks) return;
+    const bool ghost = (c == c1);
+    const int64_t k = c * Bc;
+    const int qq = q * q;
+    for (int i = threadIdx.x; i < qq; i += blockDim.x) {
+        Dt[c * qq + i] = Dw[k * qq + i];
+        if (!ghost) Et[c * qq + i] = Ew[k * qq + i];
+    }
+    const int64_t wn = (int64_t)q * ldw;
+    for (int64_t i = threadIdx.x; i < wn; i += blockDim.x) Wt[c * wn + i] = Ww[k * wn + i];
+}
+
+__global__ void top_scatter_kernel(const double* __restrict__ dst, int q, int64_t Bc, int64_t c0, int64_t c1,
+                                   int64_t nchunks, double* __restrict__ ds) {
+    const int64_t c = c0 + blockIdx.x;                 // includes the ghost c1
+    const int a = threadIdx.x;
+    if (a >= q) return;
+    ds[c * Bc * q + a] = c < nchunks ? dst[c * q + a] : 0.0;
+}
+
+__global__ void zero_outside_kernel(double* __restrict__ v, int64_t n, int64_t lo, int64_t hi) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (i < lo || i >= hi)) v[i] = 0.0;
+}
+
 // Solve the damped system for the current normal equations; delta -> dlt_c / dlt_s.
 // *ok = 0 if a Cholesky pivot was not positive.
 inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
     const int q = h->q, ldw = h->ldw;
     const int64_t nb = h->nb, nbq = nb * q;
     const size_t qq = (size_t)q * q;
+    const int64_t wn = (int64_t)q * ldw;
     double* bc = h->A.p + (size_t)h->nc * h->Pc * h->Pc;
     double* rhs = h->Sd.p + (size_t)ldw * ldw;
     int* fail_flag = h->flag.p + 1;
     MV_CUDA(h, cudaMemsetAsync(fail_flag, 0, sizeof(int), h->st));
-    damp_copy_kernel<<<(int)((nbq * q + 255) / 256), 256, 0, h->st>>>(h->D.p, h->diag_s.p, lam, nbq, q,
-                                                                      3 * h->n_ctrl, h->Dw.p);
-    MV_CUDA(h, cudaMemcpyAsync(h->Ew.p, h->E.p, nb * qq * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-    MV_CUDA(h, cudaMemcpyAsync(h->Ww.p, h->W.p, (size_t)nbq * ldw * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-    h->launches += 1;
-    // elimination levels
-    std::vector<int64_t> levels;
-    for (int64_t s = 1; s < nb; s <<= 1) levels.push_back(s);
-    for (size_t lv = 0; lv < levels.size(); ++lv) {
-        const int64_t s = levels[lv], sp = lv ? levels[lv - 1] : 0;
-        const int64_t nact = (nb + s - 1) / s;
-        launch_level(h, (int)nact, s, sp, 0, fail_flag);
-    }
-    launch_level(h, 1, levels.empty() ? 1 : levels.back() * 2, levels.empty() ? 0 : levels.back(), 1, fail_flag);
-    // Schur complement
     MV_CUDA(h, cudaMemsetAsync(h->Sd.p, 0, h->Sd.bytes(), h->st));
-    const int nts = (ldw + SY_T - 1) / SY_T, npairs = nts * (nts + 1) / 2;
-    // ~4 waves of CTAs over the SMs, slabs a multiple of the K chunk
-    int64_t nslab = std::max<int64_t>(1, (4 * h->sm_count + npairs - 1) / npairs);
-    int slab = (int)std::max<int64_t>(256, ((nbq + nslab - 1) / nslab + SY_K - 1) / SY_K * SY_K);
-    dim3 g(npairs, (unsigned)((nbq + slab - 1) / slab));
-    syrk_kernel<<<g, 512, 0, h->st>>>(h->Ww.p, nbq, ldw, slab, h->Sd.p);
-    form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
-        h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->Sd.p, rhs);
-    h->launches += 2;
-    dense_chol_solve(h, h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
-    // back substitution
-    wdc_kernel<<<(int)((nbq * 32 + 255) / 256), 256, 0, h->st>>>(h->Ww.p, h->dlt_c.p, nbq, ldw, h->dlt_s.p);
-    bcr_back_kernel<<<1, 32, 0, h->st>>>(nb, q, 0, 1, h->Dw.p, h->Ew.p, h->ZL.p, h->dlt_s.p);
-    h->launches += 2;
-    for (int lv = (int)levels.size() - 1; lv >= 0; --lv) {
-        const int64_t s = levels[lv];
-        const int64_t nel = (nb / s + 1) / 2;     // odd multiples of s below nb
-        if (nel <= 0) continue;
-        bcr_back_kernel<<<(int)nel, 32, 0, h->st>>>(nb, q, s, 0, h->Dw.p, h->Ew.p, h->ZL.p, h->dlt_s.p);
+    if (h->world <= 1) {
+        // ---------------- single GPU: full cyclic reduction + root ----------------
+        damp_copy_kernel<<<(int)((nbq * q + 255) / 256), 256, 0, h->st>>>(h->D.p, h->diag_s.p, lam, nbq, q,
+                                                                          3 * h->n_ctrl, h->Dw.p);
+        MV_CUDA(h, cudaMemcpyAsync(h->Ew.p, h->E.p, nb * qq * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+        MV_CUDA(h, cudaMemcpyAsync(h->Ww.p, h->W.p, (size_t)nbq * ldw * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+        h->launches += 1;
+        BcrView v{h->Dw.p, h->Ew.p, h->Ww.p, h->ZL.p, h->dlt_s.p, nb};
+        std::vector<int64_t> levels = bcr_eliminate(h, v, nb, true, fail_flag);
+        launch_syrk(h, h->Ww.p, nbq, h->Sd.p);
+        form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
+            h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->Sd.p, rhs);
         h->launches++;
-    }
-    MV_CUDA(h, cudaGetLastError());
-    if (h->world > 1) {
-        int e = nccl_max_flag(h, fail_flag);
-        if (!e) e = nccl_bcast0(h, h->dlt_c.p, (size_t)h->ncP);
-        if (!e) e = nccl_bcast0(h, h->dlt_s.p, (size_t)nbq);
+        dense_chol_solve(h, h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
+        wdc_kernel<<<(int)((nbq * 32 + 255) / 256), 256, 0, h->st>>>(h->Ww.p, h->dlt_c.p, nbq, ldw, h->dlt_s.p);
+        h->launches++;
+        bcr_back(h, v, levels, true);
+    } else {
+        // ---------------- sharded solve ----------------
+        // Super-blocks are cut into chunks of Bc (power of two); this rank owns chunks [c0, c1).
+        // Local levels (strides < Bc) run on the view [lo, hi] whose last block is a zeroed GHOST of
+        // the next rank's first block: it collects the left-side Schur updates.  The chunk heads
+        // form the top system (nchunks blocks), summed over ranks and eliminated redundantly.
+        const int64_t Bc = h->Bc, nchunks = nb / Bc;
+        const int64_t c0 = nchunks * h->rank / h->world, c1 = nchunks * (h->rank + 1) / h->world;
+        const int64_t lo = c0 * Bc, hi = c1 * Bc, nloc = hi - lo;
+        // damped working copies of the own range; ghost slot zero
+        if (nloc > 0) {
+            damp_copy_kernel<<<(int)((nloc * q * q + 255) / 256), 256, 0, h->st>>>(
+                h->D.p + lo * qq, h->diag_s.p + lo * q, lam, nloc * q, q,
+                std::max<int64_t>(0, 3 * h->n_ctrl - lo * q), h->Dw.p + lo * qq);
+            MV_CUDA(h, cudaMemcpyAsync(h->Ew.p + lo * qq, h->E.p + lo * qq, nloc * qq * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+            MV_CUDA(h, cudaMemcpyAsync(h->Ww.p + lo * wn, h->W.p + lo * wn, (size_t)nloc * wn * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+            h->launches++;
+        }
+        MV_CUDA(h, cudaMemsetAsync(h->Dw.p + hi * qq, 0, qq * sizeof(double), h->st));
+        MV_CUDA(h, cudaMemsetAsync(h->Ew.p + hi * qq, 0, qq * sizeof(double), h->st));
+        MV_CUDA(h, cudaMemsetAsync(h->Ww.p + hi * wn, 0, wn * sizeof(double), h->st));
+        BcrView lv{h->Dw.p + lo * qq, h->Ew.p + lo * qq, h->Ww.p + lo * wn, h->ZL.p + lo * qq, h->dlt_s.p + lo * q, nloc + 1};
+        std::vector<int64_t> llev;
+        if (nloc > 0 && Bc > 1) {
+            llev = bcr_eliminate(h, lv, Bc, false, fail_flag);
+            launch_level(h, lv, (int)((lv.nb + Bc - 1) / Bc), Bc, Bc / 2, 2, fail_flag);     // pending updates of the last local level
+        }
+        // top system
+        const size_t tD = (size_t)nchunks * qq, tW = (size_t)nchunks * wn;
+        MV_CUDA(h, cudaMemsetAsync(h->Dt.p, 0, (2 * tD + tW) * sizeof(double), h->st));
+        double* Dt = h->Dt.p; double* Et = Dt + tD; double* Wt = Et + tD;
+        if (nloc > 0) {
+            top_gather_kernel<<<(int)(c1 - c0 + 1), 128, 0, h->st>>>(h->Dw.p, h->Ew.p, h->Ww.p, q, ldw, Bc, c0, c1, nchunks, Dt, Et, Wt);
+            h->launches++;
+            // chunk heads leave the local system: their rows must not enter the local SYRK
+            MV_CUDA(h, cudaMemset2DAsync(h->Ww.p + lo * wn, (size_t)Bc * wn * sizeof(double), 0, wn * sizeof(double), (size_t)(c1 - c0), h->st));
+        }
+        int e = nccl_sum(h, Dt, 2 * tD + tW);
+        if (e) return e;
+        BcrView tv{Dt, Et, Wt, h->ZLt.p, h->dst.p, nchunks};
+        std::vector<int64_t> tlev = bcr_eliminate(h, tv, nchunks, true, fail_flag);
+        // Schur complement: local rows (+ the replicated top rows once, on rank 0), summed over ranks
+        launch_syrk(h, h->Ww.p + lo * wn, nloc * q, h->Sd.p);
+        if (h->rank == 0) launch_syrk(h, Wt, nchunks * q, h->Sd.p);
+        e = nccl_sum(h, h->Sd.p, (size_t)ldw * ldw);
+        if (e) return e;
+        form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
+            h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->Sd.p, rhs);
+        h->launches++;
+        dense_chol_solve(h, h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
+        e = nccl_bcast0(h, h->dlt_c.p, (size_t)h->ncP);
+        if (e) return e;
+        // back substitution: top system (redundant), then the local levels
+        wdc_kernel<<<(int)((nchunks * q * 32 + 255) / 256), 256, 0, h->st>>>(Wt, h->dlt_c.p, nchunks * q, ldw, h->dst.p);
+        h->launches++;
+        bcr_back(h, tv, tlev, true);
+        if (nloc > 0) {
+            wdc_kernel<<<(int)((nloc * q * 32 + 255) / 256), 256, 0, h->st>>>(h->Ww.p + lo * wn, h->dlt_c.p, nloc * q, ldw, h->dlt_s.p + lo * q);
+            top_scatter_kernel<<<(int)(c1 - c0 + 1), 32, 0, h->st>>>(h->dst.p, q, Bc, c0, c1, nchunks, h->dlt_s.p);
+            h->launches += 2;
+            bcr_back(h, lv, llev, false);
+        }
+        zero_outside_kernel<<<(int)(((nbq + q) + 255) / 256), 256, 0, h->st>>>(h->dlt_s.p, nbq + q, lo * q, hi * q);
+        h->launches++;
+        e = nccl_sum(h, h->dlt_s.p, (size_t)nbq);
+        if (!e) e = nccl_max_flag(h, fail_flag);
         if (e) return e;
     }
+    MV_CUDA(h, cudaGetLastError());
     int f = 0;
     MV_CUDA(h, cudaMemcpyAsync(&f, fail_flag, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     MV_CUDA(h, cudaStreamSynchronize(h->st));

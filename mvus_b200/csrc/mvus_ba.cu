@@ -71,7 +71,7 @@ extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
                     &h->int_b, &h->knots, &h->spanpoly, &h->span_t0, &h->lut_t0, &h->lut_invh, &h->tau,
                     &h->x, &h->x_trial, &h->camprep, &h->r, &h->J, &h->mJ, &h->partial, &h->A, &h->D, &h->E,
                     &h->W, &h->Dw, &h->Ew, &h->Ww, &h->ZL, &h->Sd, &h->dlt_c, &h->dlt_s, &h->diag_c,
-                    &h->diag_s, &h->gvec, &h->xs, &h->scratch})
+                    &h->diag_s, &h->gvec, &h->xs, &h->scratch, &h->Dt, &h->ZLt, &h->dst})
         b->release();
     for (auto* b : {&h->row_off, &h->tile_start, &h->knot_off, &h->ctrl_off, &h->xoff, &h->lut_off}) b->release();
     for (auto* b : {&h->tile_cam, &h->tile_cnt, &h->ncoef, &h->deg, &h->lut_n, &h->lut, &h->tau_spl, &h->span,
