@@ -77,6 +77,7 @@ struct mvus_ba_ctx {
     int64_t nb = 0;               // super-blocks
     int ncP = 0, ldw = 0;         // camera unknowns, leading dimension of W~ (ncP + 1 rhs column)
     mvus::DevBuf<double> A, D, E, W, Dw, Ew, Ww, ZL, Sd, dlt_c, dlt_s, diag_c, diag_s, gvec, xs;
+    mvus::DevBuf<double> bs;             // spline right-hand side (-J^T r) as a contiguous vector
     mvus::DevBuf<double> Dt, ZLt, dst;   // top-level system of the sharded solve
     int64_t Bc = 1;                      // chunk size (super-blocks) of the sharded solve
     int launches = 0;

@@ -21,6 +21,8 @@ typedef int (*fn_init)(void**, int, nccl_uid_t, int);
 typedef int (*fn_destroy)(void*);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
 typedef const char* (*fn_errstr)(int);
+typedef int (*fn_reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t);
+typedef int (*fn_group)(void);
 
 struct NcclApi {
     void* lib = nullptr;
@@ -29,6 +31,8 @@ struct NcclApi {
     fn_destroy CommDestroy = nullptr;
     fn_allreduce AllReduce = nullptr;
     fn_errstr GetErrorString = nullptr;
+    fn_reduce Reduce = nullptr;
+    fn_group GroupStart = nullptr, GroupEnd = nullptr;
     bool load(std::string& err) {
         if (lib) return true;
         const char* names[] = {"libnccl.so.2", "libnccl.so"};
@@ -42,6 +46,9 @@ struct NcclApi {
         CommDestroy = (fn_destroy)dlsym(lib, "ncclCommDestroy");
         AllReduce = (fn_allreduce)dlsym(lib, "ncclAllReduce");
         GetErrorString = (fn_errstr)dlsym(lib, "ncclGetErrorString");
+        Reduce = (fn_reduce)dlsym(lib, "ncclReduce");
+        GroupStart = (fn_group)dlsym(lib, "ncclGroupStart");
+        GroupEnd = (fn_group)dlsym(lib, "ncclGroupEnd");
         if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce) { err = "libnccl lacks required symbols"; return false; }
         return true;
     }
@@ -64,31 +71,41 @@ inline int nccl_sum(mvus_ba_ctx* h, double* buf, size_t count) {
     return MVUS_OK;
 }
 
-inline int allreduce_normal_equations(mvus_ba_ctx* h) {
-    if (h->world <= 1) return MVUS_OK;
-    const size_t qq = (size_t)h->q * h->q;
-    int rc = nccl_sum(h, h->A.p, (size_t)h->nc * h->Pc * h->Pc + h->ncP);
-    if (!rc) rc = nccl_sum(h, h->D.p, h->nb * qq);
-    if (!rc) rc = nccl_sum(h, h->E.p, h->nb * qq);
-    if (!rc) rc = nccl_sum(h, h->W.p, (size_t)h->nb * h->q * h->ldw);
-    return rc;
+// block range [lo, hi) of super-blocks owned by rank r in the sharded solve
+inline void owner_range(const mvus_ba_ctx* h, int r, int64_t* lo, int64_t* hi) {
+    const int64_t nchunks = h->nb / h->Bc;
+    *lo = nchunks * r / h->world * h->Bc;
+    *hi = nchunks * (r + 1) / h->world * h->Bc;
 }
 
-// Make rank 0's copy of a buffer the copy of every rank (zero elsewhere + sum): the redundant
-// solve uses split-K atomics whose summation order is not fixed, so steps could differ in the
-// last bits between ranks; broadcasting keeps x and every accept/reject decision identical.
-inline int nccl_bcast0(mvus_ba_ctx* h, double* buf, size_t count) {
-    if (h->world <= 1 || count == 0) return MVUS_OK;
-    if (h->rank != 0) {
-        cudaError_t e = cudaMemsetAsync(buf, 0, count * sizeof(double), h->st);
-        if (e != cudaSuccess) return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e));
-    }
-    return nccl_sum(h, buf, count);
-}
-inline int nccl_max_flag(mvus_ba_ctx* h, int* flag) {
+// Sum the per-rank normal equations.  Camera blocks (small) are all-reduced.  The spline-side
+// arrays D, E, W~ (2.8 GB at config 4) are only needed by the rank that owns the block range in
+// the sharded solve, so each range is REDUCED TO ITS OWNER (grouped ncclReduce: half the wire
+// traffic of an all-reduce); `full` forces an all-reduce (diagnostic entry point).
+inline int reduce_normal_equations(mvus_ba_ctx* h, bool full) {
     if (h->world <= 1) return MVUS_OK;
-    const int rc = nccl_api().AllReduce(flag, flag, 1, 2 /*ncclInt32*/, 2 /*ncclMax*/, h->nccl_comm, h->st);
-    if (rc != 0) return fail(h, MVUS_ERR_NCCL, "ncclAllReduce(flag) failed");
+    const size_t qq = (size_t)h->q * h->q, wn = (size_t)h->q * h->ldw;
+    int rc = nccl_sum(h, h->A.p, (size_t)h->nc * h->Pc * h->Pc + h->ncP);
+    if (rc) return rc;
+    NcclApi& api = nccl_api();
+    if (full || !api.Reduce || !api.GroupStart || !api.GroupEnd) {
+        rc = nccl_sum(h, h->D.p, h->nb * qq);
+        if (!rc) rc = nccl_sum(h, h->E.p, h->nb * qq);
+        if (!rc) rc = nccl_sum(h, h->W.p, (size_t)h->nb * wn);
+        return rc;
+    }
+    int e = api.GroupStart();
+    for (int r = 0; r < h->world && e == 0; ++r) {
+        int64_t lo, hi;
+        owner_range(h, r, &lo, &hi);
+        if (hi <= lo) continue;
+        const size_t nblk = (size_t)(hi - lo);
+        e = api.Reduce(h->D.p + lo * qq, h->D.p + lo * qq, nblk * qq, NCCL_FLOAT64, NCCL_SUM, r, h->nccl_comm, h->st);
+        if (!e) e = api.Reduce(h->E.p + lo * qq, h->E.p + lo * qq, nblk * qq, NCCL_FLOAT64, NCCL_SUM, r, h->nccl_comm, h->st);
+        if (!e) e = api.Reduce(h->W.p + lo * wn, h->W.p + lo * wn, nblk * wn, NCCL_FLOAT64, NCCL_SUM, r, h->nccl_comm, h->st);
+    }
+    const int e2 = api.GroupEnd();
+    if (e || e2) return fail(h, MVUS_ERR_NCCL, "grouped ncclReduce of the normal equations failed");
     return MVUS_OK;
 }
 

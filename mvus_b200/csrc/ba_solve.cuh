@@ -240,9 +240,13 @@ __global__ void accumulate_motion_kernel(const double* __restrict__ r_motion, co
 }
 
 // Marquardt diagonals (clamped) and damped working copies.
-__global__ void diag_kernel(const double* __restrict__ A, const double* __restrict__ D, int nc, int Pc,
-                            int64_t nbq, int q, int64_t n_ctrl3, double* __restrict__ diag_c,
-                            double* __restrict__ diag_s) {
+// Marquardt diagonals (clamped) and the spline right-hand side b_s = W~[:, last] as a vector.
+// Rows outside [row_lo, row_hi) (another rank's block range) are written as 0 and filled in by
+// the all-reduce that follows.
+__global__ void diag_kernel(const double* __restrict__ A, const double* __restrict__ D,
+                            const double* __restrict__ W, int nc, int Pc, int64_t nbq, int q, int ldw,
+                            int64_t n_ctrl3, int64_t row_lo, int64_t row_hi, double* __restrict__ diag_c,
+                            double* __restrict__ diag_s, double* __restrict__ bs) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (int64_t)nc * Pc) {
         const int cam = (int)(i / Pc), p = (int)(i - (int64_t)cam * Pc);
@@ -251,8 +255,10 @@ __global__ void diag_kernel(const double* __restrict__ A, const double* __restri
     if (i < nbq) {
         const int64_t kb = i / q;
         const int l = (int)(i - kb * q);
+        const bool mine = i >= row_lo && i < row_hi;
         // padding unknowns (beyond the last control point) get a unit diagonal, no damping
-        diag_s[i] = i < n_ctrl3 ? fmin(fmax(D[(kb * q + l) * q + l], DIAG_MIN), DIAG_MAX) : 0.0;
+        diag_s[i] = (mine && i < n_ctrl3) ? fmin(fmax(D[(kb * q + l) * q + l], DIAG_MIN), DIAG_MAX) : 0.0;
+        bs[i] = mine ? W[i * ldw + (ldw - 1)] : 0.0;
     }
 }
 
@@ -739,8 +745,8 @@ __global__ void bcr_back_kernel(int64_t nb, int q, int64_t s, int root, const do
 // sums[4] = max |g| (as ordered-int atomicMax on the bits of a non-negative double)
 __global__ void step_dots_kernel(const double* __restrict__ dc, const double* __restrict__ ds,
                                  const double* __restrict__ diag_c, const double* __restrict__ diag_s,
-                                 const double* __restrict__ bc, const double* __restrict__ W, int ncP,
-                                 int64_t n_ctrl3, int ldw, const double* __restrict__ x, int64_t n,
+                                 const double* __restrict__ bc, const double* __restrict__ bs, int ncP,
+                                 int64_t n_ctrl3, const double* __restrict__ x, int64_t n,
                                  double* __restrict__ sums) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0, gm = 0;
@@ -749,7 +755,7 @@ __global__ void step_dots_kernel(const double* __restrict__ dc, const double* __
         s0 += diag_c[i] * d * d; s1 += bc[i] * d; s2 += d * d; gm = fabs(bc[i]);
     }
     if (i < n_ctrl3) {
-        const double d = ds[i], b = W[i * ldw + (ldw - 1)];
+        const double d = ds[i], b = bs[i];
         s0 += diag_s[i] * d * d; s1 += b * d; s2 += d * d; gm = fmax(gm, fabs(b));
     }
     if (i < n) s3 = x[i] * x[i];
@@ -792,8 +798,8 @@ __global__ void apply_step_kernel(const double* __restrict__ x, const double* __
 }
 
 // gradient in the reference layout: g = -b
-__global__ void gradient_kernel(const double* __restrict__ bc, const double* __restrict__ W, int nc, int C,
-                                int Pc, int64_t n_other, SplineView sp, int64_t n_ctrl, int ldw,
+__global__ void gradient_kernel(const double* __restrict__ bc, const double* __restrict__ bs, int nc, int C,
+                                int Pc, int64_t n_other, SplineView sp, int64_t n_ctrl,
                                 double* __restrict__ g) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_other) {
@@ -808,7 +814,7 @@ __global__ void gradient_kernel(const double* __restrict__ bc, const double* __r
         const int64_t l = i - sp.ctrl_off[s];
         const int nco = sp.ncoef[s];
         for (int ax = 0; ax < 3; ++ax)
-            g[sp.xoff[s] + (int64_t)ax * nco + l] = -W[(i * 3 + ax) * ldw + (ldw - 1)];
+            g[sp.xoff[s] + (int64_t)ax * nco + l] = -bs[i * 3 + ax];
     }
 }
 
@@ -873,6 +879,7 @@ inline int solver_alloc(mvus_ba_ctx* h) {
     MV_CUDA(h, h->dlt_s.alloc(((size_t)h->nb + 1) * h->q));
     MV_CUDA(h, h->diag_c.alloc(h->ncP));
     MV_CUDA(h, h->diag_s.alloc((size_t)h->nb * h->q));
+    MV_CUDA(h, h->bs.alloc(((size_t)h->nb + 1) * h->q));
     MV_CUDA(h, h->gvec.alloc(h->n));
     MV_CUDA(h, h->xs.alloc(16));
     return MVUS_OK;
@@ -909,17 +916,26 @@ inline int accumulate(mvus_ba_ctx* h) {
     return MVUS_OK;
 }
 
-int allreduce_normal_equations(mvus_ba_ctx* h);   // ba_nccl.cuh
+int reduce_normal_equations(mvus_ba_ctx* h, bool full);   // ba_nccl.cuh
+void owner_range(const mvus_ba_ctx* h, int r, int64_t* lo, int64_t* hi);
 int nccl_bcast0(mvus_ba_ctx* h, double* buf, size_t count);
 int nccl_max_flag(mvus_ba_ctx* h, int* flag);
 int nccl_sum(mvus_ba_ctx* h, double* buf, size_t count);
 
-inline int compute_diag(mvus_ba_ctx* h) {
+inline int compute_diag(mvus_ba_ctx* h, bool full_everywhere = false) {
     const int64_t nbq = h->nb * h->q;
     const int64_t cnt = std::max<int64_t>(nbq, h->ncP);
-    diag_kernel<<<(int)((cnt + 255) / 256), 256, 0, h->st>>>(h->A.p, h->D.p, h->nc, h->Pc, nbq, h->q,
-                                                            3 * h->n_ctrl, h->diag_c.p, h->diag_s.p);
+    int64_t lo = 0, hi = h->nb;
+    if (h->world > 1 && !full_everywhere) owner_range(h, h->rank, &lo, &hi);
+    diag_kernel<<<(int)((cnt + 255) / 256), 256, 0, h->st>>>(h->A.p, h->D.p, h->W.p, h->nc, h->Pc, nbq, h->q,
+                                                            h->ldw, 3 * h->n_ctrl, lo * h->q, hi * h->q,
+                                                            h->diag_c.p, h->diag_s.p, h->bs.p);
     h->launches++;
+    if (h->world > 1 && !full_everywhere) {
+        int e = nccl_sum(h, h->diag_s.p, (size_t)nbq);
+        if (!e) e = nccl_sum(h, h->bs.p, (size_t)nbq);
+        if (e) return e;
+    }
     const int64_t n3 = 3 * h->n_ctrl;
     if (n3 > 0) {
         MV_CUDA(h, cudaMemsetAsync(h->xs.p + 8, 0, sizeof(double), h->st));

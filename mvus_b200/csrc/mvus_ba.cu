@@ -71,7 +71,7 @@ extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
                     &h->int_b, &h->knots, &h->spanpoly, &h->span_t0, &h->lut_t0, &h->lut_invh, &h->tau,
                     &h->x, &h->x_trial, &h->camprep, &h->r, &h->J, &h->mJ, &h->partial, &h->A, &h->D, &h->E,
                     &h->W, &h->Dw, &h->Ew, &h->Ww, &h->ZL, &h->Sd, &h->dlt_c, &h->dlt_s, &h->diag_c,
-                    &h->diag_s, &h->gvec, &h->xs, &h->scratch, &h->Dt, &h->ZLt, &h->dst})
+                    &h->diag_s, &h->gvec, &h->xs, &h->scratch, &h->Dt, &h->ZLt, &h->dst, &h->bs})
         b->release();
     for (auto* b : {&h->row_off, &h->tile_start, &h->knot_off, &h->ctrl_off, &h->xoff, &h->lut_off}) b->release();
     for (auto* b : {&h->tile_cam, &h->tile_cnt, &h->ncoef, &h->deg, &h->lut_n, &h->lut, &h->tau_spl, &h->span,
@@ -381,8 +381,8 @@ static int step_scalars(mvus_ba_ctx* h, const double* xd, double out[5]) {
     const int64_t cnt = std::max<int64_t>(h->n, std::max<int64_t>(3 * h->n_ctrl, h->ncP));
     double* bc = h->A.p + (size_t)h->nc * h->Pc * h->Pc;
     step_dots_kernel<<<(int)((cnt + 255) / 256), 256, 0, h->st>>>(h->dlt_c.p, h->dlt_s.p, h->diag_c.p,
-                                                                  h->diag_s.p, bc, h->W.p, h->ncP,
-                                                                  3 * h->n_ctrl, h->ldw, xd, h->n, h->xs.p);
+                                                                  h->diag_s.p, bc, h->bs.p, h->ncP,
+                                                                  3 * h->n_ctrl, xd, h->n, h->xs.p);
     h->launches++;
     MV_CUDA(h, cudaMemcpyAsync(h->h_pin, h->xs.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     MV_CUDA(h, cudaStreamSynchronize(h->st));
@@ -466,7 +466,7 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
         if (need_accum) {
             PhaseTimer t(h, 2, &st.ms_accum);
             rc = accumulate(h);
-            if (!rc) rc = allreduce_normal_equations(h);
+            if (!rc) rc = reduce_normal_equations(h, false);
             if (!rc) rc = compute_diag(h);
             t.stop();
             if (rc) return rc;
@@ -601,7 +601,8 @@ extern "C" int mvus_ba_normal_equations(mvus_ba_handle h, const double* x, doubl
     rc = check_motion_flag(h);
     if (rc) return rc;
     rc = accumulate(h);
-    if (!rc) rc = allreduce_normal_equations(h);
+    if (!rc) rc = reduce_normal_equations(h, true);      // diagnostics: every rank gets everything
+    if (!rc) rc = compute_diag(h, true);
     if (rc) return rc;
     if (cost) *cost = F;
     const int q = h->q, bw = h->bw, ldw = h->ldw, Pc = h->Pc;
@@ -610,7 +611,7 @@ extern "C" int mvus_ba_normal_equations(mvus_ba_handle h, const double* x, doubl
     if (g) {
         double* bc = h->A.p + (size_t)h->nc * Pc * Pc;
         gradient_kernel<<<(int)((std::max<int64_t>(h->n_other, h->n_ctrl) + 255) / 256), 256, 0, h->st>>>(
-            bc, h->W.p, h->nc, h->C, Pc, h->n_other, h->sv, h->n_ctrl, ldw, h->gvec.p);
+            bc, h->bs.p, h->nc, h->C, Pc, h->n_other, h->sv, h->n_ctrl, h->gvec.p);
         MV_CUDA(h, cudaMemcpyAsync(g, h->gvec.p, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     }
     MV_CUDA(h, cudaStreamSynchronize(h->st));
