@@ -109,6 +109,25 @@ inline int reduce_normal_equations(mvus_ba_ctx* h, bool full) {
     return MVUS_OK;
 }
 
+// Make rank 0's copy of a buffer the copy of every rank (zero elsewhere + sum): the Cholesky of
+// the reduced system is computed redundantly from split-K partial sums whose order is not fixed,
+// so it could differ in the last bits between ranks; broadcasting keeps x and every
+// accept/reject decision identical.
+inline int nccl_bcast0(mvus_ba_ctx* h, double* buf, size_t count) {
+    if (h->world <= 1 || count == 0) return MVUS_OK;
+    if (h->rank != 0) {
+        cudaError_t e = cudaMemsetAsync(buf, 0, count * sizeof(double), h->st);
+        if (e != cudaSuccess) return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e));
+    }
+    return nccl_sum(h, buf, count);
+}
+inline int nccl_max_flag(mvus_ba_ctx* h, int* flag) {
+    if (h->world <= 1) return MVUS_OK;
+    const int rc = nccl_api().AllReduce(flag, flag, 1, 2 /*ncclInt32*/, 2 /*ncclMax*/, h->nccl_comm, h->st);
+    if (rc != 0) return fail(h, MVUS_ERR_NCCL, "ncclAllReduce(flag) failed");
+    return MVUS_OK;
+}
+
 // sum of squares lives at partial[cost_slot]; make it the global sum
 inline int allreduce_cost_slot(mvus_ba_ctx* h) {
     return nccl_sum(h, h->partial.p + h->cost_slot, 1);

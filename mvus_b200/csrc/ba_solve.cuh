@@ -916,11 +916,11 @@ inline int accumulate(mvus_ba_ctx* h) {
     return MVUS_OK;
 }
 
-int reduce_normal_equations(mvus_ba_ctx* h, bool full);   // ba_nccl.cuh
-void owner_range(const mvus_ba_ctx* h, int r, int64_t* lo, int64_t* hi);
-int nccl_bcast0(mvus_ba_ctx* h, double* buf, size_t count);
-int nccl_max_flag(mvus_ba_ctx* h, int* flag);
-int nccl_sum(mvus_ba_ctx* h, double* buf, size_t count);
+inline int reduce_normal_equations(mvus_ba_ctx* h, bool full);   // ba_nccl.cuh
+inline void owner_range(const mvus_ba_ctx* h, int r, int64_t* lo, int64_t* hi);
+inline int nccl_bcast0(mvus_ba_ctx* h, double* buf, size_t count);
+inline int nccl_max_flag(mvus_ba_ctx* h, int* flag);
+inline int nccl_sum(mvus_ba_ctx* h, double* buf, size_t count);
 
 inline int compute_diag(mvus_ba_ctx* h, bool full_everywhere = false) {
     const int64_t nbq = h->nb * h->q;
@@ -1142,6 +1142,5 @@ inline int read_cost(mvus_ba_ctx* h, double* cost) {
     return MVUS_OK;
 }
 
-int allreduce_cost(mvus_ba_ctx* h, double* cost);   // ba_nccl.cuh
 
 }  // namespace mvus
