@@ -256,9 +256,12 @@ def test_full_size_cfg2_recovers_ground_truth(built_lib):
     C_gt = np.array([-R.T @ t for R, t in zip(truth['R'], truth['t'])]).T
     from scipy import interpolate
     from mvus_b200 import synth
-    tt = np.linspace(fl.spline['int'][0, 0] + 50, fl.spline['int'][1, -1] - 50, 2000)
+    tt = np.linspace(200.0, truth['T'] - 200.0, 2000)     # where detections constrain the spline
     X_est = np.asarray(interpolate.splev(tt, fl.spline['tck'][0]))
-    X_gt = synth.gt_trajectory(tt)
+    # time gauge: a global time t of the estimate is frame (t - beta0)/alpha0 of the reference
+    # camera, whose true global time is alpha0_true * frame + beta0_true (all betas may drift together)
+    t_true = truth['alpha'][0] * (tt - fl.beta[0]) / fl.alpha[0] + truth['beta'][0]
+    X_gt = synth.gt_trajectory(t_true)
     P, Q = np.hstack((C_est, X_est)), np.hstack((C_gt, X_gt))
     mp, mq = P.mean(1, keepdims=True), Q.mean(1, keepdims=True)
     U, S, Vt = np.linalg.svd((Q - mq) @ (P - mp).T)
