@@ -210,9 +210,14 @@ def main():
     # ---- end to end through the public API (host buffers) -----------------------------------
     if world > 1:
         dist.barrier()
+    # one untimed call first (warm-up: pinned output pool, CUDA context paths), then restore the
+    # initial parameters so that the timed call does the same work from the same start
+    ba.bundle_adjust(fl, fl.numCam, max_iter=2, ftol=0.0, xtol=0.0, gtol=0.0, **BA_KW)
+    fp.unpack_into(fl, fp.x0)
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
-    res = fl.BA(fl.numCam, max_iter=a.steps + 1, ftol=0.0, xtol=0.0, gtol=0.0, **BA_KW) \
-        if False else ba.bundle_adjust(fl, fl.numCam, max_iter=a.steps + 1, ftol=0.0, xtol=0.0, gtol=0.0, **BA_KW)
+    res = ba.bundle_adjust(fl, fl.numCam, max_iter=a.steps + 1, ftol=0.0, xtol=0.0, gtol=0.0, **BA_KW)
     torch.cuda.synchronize()
     dt_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -253,7 +258,7 @@ def main():
             'resid_jac_mdet_per_s': N_total / (ms[1] / 1e3) / 1e6,
             'roofline': roof, 'phases': phases, 'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'seconds': dt_e2e, 'steps': e2e_steps},
+                    'seconds': dt_e2e, 'steps': e2e_steps, 'host_phases_ms': res.stats.get('host')},
             'gpu_launches': int(st.launches), 'linear_solves': int(st.lm_iterations), 'final_cost': st.cost, 'cost0': st.cost0,
             'workload_gen_s': t_gen}
     if world == 1 and not a.no_cpu_baseline:

@@ -149,6 +149,15 @@ int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, double* r_o
  * array the reference stores in Scene.detections_global[i] (np.vstack, common.py:127). */
 int mvus_ba_detections_global(mvus_ba_handle h, const double* x, double* out);
 
+/* Scene.visible (compute_visibility, common.py:427-438) of the optimised cameras at parameters
+ * x: 1-based spline-interval id per detection, 0 = in no interval (util.sampling belong=True,
+ * util.py:103-106).  visible[N] int64, concatenated in camera order. */
+int mvus_ba_visibility(mvus_ba_handle h, const double* x, int64_t* visible);
+
+/* Page-locked host buffers for large outputs (device->host copies at PCIe speed). */
+void* mvus_ba_host_alloc(size_t bytes);
+void  mvus_ba_host_free(void* p);
+
 /* Bookkeeping output of Scene.all_detect_to_traj (common.py:887-944) at parameters x:
  * `global_traj` = every detection of the optimised cameras whose global time stamp lies inside
  * a spline interval (closed ends, common.py:292), sorted by time stamp.  out: 7 x n_out

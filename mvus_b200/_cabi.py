@@ -38,7 +38,8 @@ class BAStats(ctypes.Structure):
 EXPORTS = ['mvus_ba_version', 'mvus_ba_create', 'mvus_ba_destroy', 'mvus_ba_last_error',
            'mvus_ba_set_detections', 'mvus_ba_set_detections_rows', 'mvus_ba_set_splines', 'mvus_ba_dims', 'mvus_ba_residual',
            'mvus_ba_residual_jacobian', 'mvus_ba_solve', 'mvus_ba_detections_global',
-           'mvus_ba_normal_equations', 'mvus_ba_global_traj', 'mvus_ba_nccl_unique_id', 'mvus_ba_comm_init',
+           'mvus_ba_normal_equations', 'mvus_ba_global_traj', 'mvus_ba_visibility', 'mvus_ba_host_alloc',
+           'mvus_ba_host_free', 'mvus_ba_nccl_unique_id', 'mvus_ba_comm_init',
            'mvus_ba_time_resjac', 'mvus_ba_time_accumulate']
 
 _lib = None
@@ -74,12 +75,55 @@ def load():
     lib.mvus_ba_detections_global.argtypes = [ctypes.c_void_p, _dp, _dp]
     lib.mvus_ba_normal_equations.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp, _ip, _dp, _dp]
     lib.mvus_ba_global_traj.argtypes = [ctypes.c_void_p, _dp, _ip, _lp, _dp]
+    lib.mvus_ba_visibility.argtypes = [ctypes.c_void_p, _dp, _lp]
+    lib.mvus_ba_host_alloc.argtypes = [ctypes.c_size_t]
+    lib.mvus_ba_host_alloc.restype = ctypes.c_void_p
+    lib.mvus_ba_host_free.argtypes = [ctypes.c_void_p]
+    lib.mvus_ba_host_free.restype = None
     lib.mvus_ba_nccl_unique_id.argtypes = [ctypes.c_char_p]
     lib.mvus_ba_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p]
     lib.mvus_ba_time_resjac.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int32, _dp]
     lib.mvus_ba_time_accumulate.argtypes = [ctypes.c_void_p, ctypes.c_int32, _dp]
     _lib = lib
     return lib
+
+
+class PinnedPool:
+    """Grow-only pool of page-locked host blocks for the big outputs.  `empty(n, dtype)` returns a
+    NumPy array living in pinned memory; when the array (and every view of it) is garbage
+    collected the block returns to the pool, so repeated BA calls (main.py makes 2 per camera)
+    reuse the same pages.  Falls back to pageable memory if pinning fails or the cap is hit."""
+    CAP_BYTES = 24 << 30
+
+    def __init__(self):
+        self.free = []          # (nbytes, ptr)
+        self.total = 0
+
+    def empty(self, n, dtype=np.float64):
+        import weakref
+        nbytes = max(int(n) * np.dtype(dtype).itemsize, 8)
+        lib = load()
+        ptr = None
+        for k, (sz, p) in enumerate(self.free):
+            if nbytes <= sz <= 2 * nbytes + (1 << 20):
+                ptr, cap = p, sz
+                del self.free[k]
+                break
+        if ptr is None:
+            if self.total + nbytes > self.CAP_BYTES:
+                return np.empty(int(n), dtype=dtype)
+            ptr = lib.mvus_ba_host_alloc(nbytes)
+            if not ptr:
+                return np.empty(int(n), dtype=dtype)
+            cap = nbytes
+            self.total += nbytes
+        buf = (ctypes.c_char * cap).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(n))
+        weakref.finalize(buf, self.free.append, (cap, ptr))
+        return arr
+
+
+POOL = PinnedPool()
 
 
 def _d(a):
@@ -164,23 +208,31 @@ class Handle:
     def solve(self, x0, want_r=True):
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         x = np.empty(self.n)
-        r = np.empty(self.m) if want_r else None
+        r = POOL.empty(self.m) if want_r else None
         st = BAStats()
         self._check(self.lib.mvus_ba_solve(self.h, _d(x0), _d(x), _d(r), ctypes.byref(st)))
         return x, r, st
 
     def detections_global(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
-        out = np.empty(3 * self.N)
+        out = POOL.empty(3 * self.N)
         self._check(self.lib.mvus_ba_detections_global(self.h, _d(x), _d(out)))
         # zero-copy 3 x N_i views, one per camera: the arrays Scene.detections_global holds
         cp = self.fp.cam_ptr
         return [out[3 * cp[k]:3 * cp[k + 1]].reshape(3, -1) for k in range(self.fp.nc)]
 
+    def visibility(self, x):
+        """Per camera: int64 array, 1-based interval id of each detection, 0 = none."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = POOL.empty(self.N, dtype=np.int64)
+        self._check(self.lib.mvus_ba_visibility(self.h, _d(x), _l(out)))
+        cp = self.fp.cam_ptr
+        return [out[cp[k]:cp[k + 1]] for k in range(self.fp.nc)]
+
     def global_traj(self, x, cam_ids):
         x = np.ascontiguousarray(x, dtype=np.float64)
         ids = np.ascontiguousarray(cam_ids, dtype=np.int32)
-        out = np.empty(7 * max(self.N, 1))
+        out = POOL.empty(7 * max(self.N, 1))
         n = ctypes.c_int64()
         self._check(self.lib.mvus_ba_global_traj(self.h, _d(x), _i(ids), ctypes.byref(n), _d(out)))
         return out[:7 * n.value].reshape(7, n.value)

@@ -185,15 +185,15 @@ def _all_detect_to_traj(scene, fp, hd, x):
     in-interval detections with their spline positions) from the device (mvus_ba_global_traj)."""
     cams = fp.seq
     N = fp.N
-    gd = np.empty((3, N))
+    gd = _cabi.POOL.empty(3 * N).reshape(3, N)
     for k, i in enumerate(cams):
         a, b = fp.cam_ptr[k], fp.cam_ptr[k + 1]
         gd[0, a:b] = i
         gd[1, a:b] = fp.dets[k][0]
         gd[2, a:b] = scene.detections_global[i][0]
     scene.global_detections = gd
-    scene.frame_id_all = gd[1].copy()
-    scene.global_time_stamps_all = gd[2].copy()
+    scene.frame_id_all = gd[1]                 # views of global_detections (same values, no copy)
+    scene.global_time_stamps_all = gd[2]
     scene.global_traj = hd.global_traj(x, cams)
 
 
@@ -208,16 +208,25 @@ def bundle_adjust(scene, numCam, max_iter=10, rs=False, motion_prior=False, moti
                                   'never used by main.py and is not implemented; see SURVEY.md 8b')
     assert len(scene.alpha) == scene.numCam and len(scene.beta) == scene.numCam, \
         'The Number of alpha and beta is wrong'
+    import time as _time
+    _t = [_time.perf_counter()]
+    host = {}
+
+    def lap(name):
+        _t.append(_time.perf_counter())
+        host[name] = host.get(name, 0.0) + (_t[-1] - _t[-2]) * 1e3
+
     fp = FlatProblem(scene, numCam, rs=rs, motion_reg=motion_reg, motion_weights=motion_weights,
                      rs_bounds=rs_bounds, max_iter=max_iter)
+    lap('pack_ms')
     print('Number of BA parameters is {}'.format(fp.n))
     interval = np.asarray(scene.spline['int'], dtype=np.float64)
     others = [i for i in range(scene.numCam) if i not in fp.seq]
 
-    def refresh(hd, x, with_visible):
-        """detections_global (and visible) of the optimised cameras from the BA handle itself
-        (one upload of the detections serves visibility, solve and refresh); cameras outside
-        sequence[:numCam] go through a second, small handle."""
+    def refresh(hd, x):
+        """detections_global of the optimised cameras from the BA handle itself (one upload of
+        the detections serves visibility, solve and refresh); cameras outside sequence[:numCam]
+        go through a second, small handle."""
         new = hd.detections_global(x)
         dg = list(scene.detections_global) if len(scene.detections_global) == scene.numCam \
             else [[] for _ in range(scene.numCam)]
@@ -226,22 +235,36 @@ def bundle_adjust(scene, numCam, max_iter=10, rs=False, motion_prior=False, moti
         scene.detections_global = dg
         if others:
             detection_to_global(scene, others)
-        if with_visible:
-            scene.visible = [_interval_membership(scene.detections_global[i][0], interval)
-                             for i in range(scene.numCam)]
+
+    def visibility(hd, x):
+        """Scene.visible with the PRE-BA parameters (common.py:493): interval ids from the device
+        for the optimised cameras, host membership test for the (few) remaining ones."""
+        vis = [None] * scene.numCam
+        for k, v in zip(fp.seq, hd.visibility(x)):
+            vis[k] = v
+        if others:
+            detection_to_global(scene, others)
+            for i in others:
+                vis[i] = _interval_membership(scene.detections_global[i][0], interval)
+        scene.visible = vis
 
     print('Doing BA with {} cameras...\n'.format(numCam))
     hd = _cabi.Handle(fp, device=DEVICE, ftol=ftol, xtol=xtol, gtol=gtol)
+    lap('upload_ms')
     try:
         if _COMM is not None and _COMM[0] > 1:
             hd.comm_init(*_COMM)
-        refresh(hd, fp.x0, True)            # visibility with PRE-BA parameters (common.py:493)
+        visibility(hd, fp.x0)               # common.py:493
+        lap('visibility_ms')
         x, r, st = hd.solve(fp.x0)
+        lap('solve_ms')
         fp.unpack_into(scene, x)            # common.py:672-692
-        refresh(hd, x, False)               # common.py:695
+        refresh(hd, x)                      # common.py:695
+        lap('refresh_ms')
         if motion_reg and bookkeeping:
             _all_detect_to_traj(scene, fp, hd, x)
             spline_to_traj(scene)           # common.py:379 leaves traj = unit-step samples
+            lap('bookkeeping_ms')
     finally:
         if not return_handle:
             hd.close()
@@ -250,6 +273,7 @@ def bundle_adjust(scene, numCam, max_iter=10, rs=False, motion_prior=False, moti
                          active_mask=np.zeros(fp.n, dtype=int), nfev=st.nfev, njev=st.njev,
                          status=st.status, message=_MESSAGES.get(st.status, ''), success=st.status > 0)
     res.stats = st.as_dict()
+    res.stats['host'] = host
     if return_handle:
         res.handle = hd
     return res

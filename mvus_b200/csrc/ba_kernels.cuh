@@ -188,4 +188,17 @@ __global__ void det_global_kernel(const double* __restrict__ camprep, const int*
     } else { *u = obs_u[d]; *v = obs_v[d]; }
 }
 
+// visible[d] = 1-based interval id of detection d's time stamp, 0 if none (util.py:103-106)
+__global__ void visibility_kernel(SplineView sp, const double* __restrict__ camprep, const int* __restrict__ tile_cam,
+                                  const int64_t* __restrict__ tile_start, const int* __restrict__ tile_cnt,
+                                  const double* __restrict__ frame, const double* __restrict__ yr,
+                                  long long* __restrict__ visible) {
+    const int tl = blockIdx.x;
+    if ((int)threadIdx.x >= tile_cnt[tl]) return;
+    const CamPrep& c = *reinterpret_cast<const CamPrep*>(camprep + (size_t)tile_cam[tl] * CAMPREP_DOUBLES);
+    const int64_t d = tile_start[tl] + threadIdx.x;
+    const double t = c.alpha * (frame[d] + c.rho * (yr[d] * c.invH)) + c.beta;
+    visible[d] = (long long)(find_interval(sp, t) + 1);
+}
+
 }  // namespace mvus

@@ -726,3 +726,33 @@ extern "C" int mvus_ba_global_traj(mvus_ba_handle h, const double* x, const int3
     if (e != cudaSuccess) return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e));
     return MVUS_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Pinned host memory for the large outputs (detections_global, residuals, global_traj): pageable
+// device->host copies measured ~4 GB/s on the GPU box, pinned ones run at PCIe speed.
+extern "C" void* mvus_ba_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void mvus_ba_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// visible (Scene.compute_visibility, common.py:427-438): 1-based interval id per detection at x,
+// 0 = covered by no interval -- util.sampling(..., belong=True) (util.py:103-106).
+extern "C" int mvus_ba_visibility(mvus_ba_handle h, const double* x, int64_t* visible) {
+    int rc = check_ready(h);
+    if (rc) return rc;
+    if (!x || !visible) return fail(h, MVUS_ERR_ARG, "null argument");
+    if (h->N == 0) return MVUS_OK;
+    MV_CUDA(h, cudaMemcpyAsync(h->x.p, x, h->n * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    cam_prep_kernel<<<(h->nc + 63) / 64, 64, 0, h->st>>>(h->x.p, h->nc, h->C, h->desc.opt_calib, h->calib.p,
+                                                         h->height.p, h->camprep.p);
+    MV_CUDA(h, h->scratch.alloc((size_t)h->N));
+    visibility_kernel<<<h->n_tiles, TILE_DET, 0, h->st>>>(h->sv, h->camprep.p, h->tile_cam.p, h->tile_start.p,
+                                                         h->tile_cnt.p, h->frame.p, h->yr.p,
+                                                         reinterpret_cast<long long*>(h->scratch.p));
+    MV_CUDA(h, cudaGetLastError());
+    MV_CUDA(h, cudaMemcpyAsync(visible, h->scratch.p, (size_t)h->N * sizeof(int64_t), cudaMemcpyDeviceToHost, h->st));
+    MV_CUDA(h, cudaStreamSynchronize(h->st));
+    return MVUS_OK;
+}

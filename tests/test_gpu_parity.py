@@ -149,7 +149,11 @@ def test_scene_ba_postconditions(built_lib):
     """Scene.BA drop-in: reference signature, post-conditions of SURVEY.md 8b."""
     fl, truth, bakw = cases.make('rs_F_gap')
     det_before = [d.copy() for d in fl.detections]
+    prob0 = ba_oracle.Problem(fl, fl.numCam, **bakw)
+    vis0 = [prob0.membership(prob0._cam_terms(prob0.x0, i)['t']) for i in range(fl.numCam)]
     res = fl.BA(fl.numCam, max_iter=15, **bakw)
+    for i in range(fl.numCam):                       # visible = membership at the PRE-BA parameters
+        assert np.array_equal(np.asarray(fl.visible[i]), vis0[i])
     for k in ('x', 'cost', 'fun', 'nfev', 'njev', 'status', 'optimality'):
         assert hasattr(res, k)
     assert res.nfev <= 15
