@@ -216,6 +216,7 @@ def main():
     fp.unpack_into(fl, fp.x0)
     if world > 1:
         dist.barrier()
+    pool0 = (_cabi.POOL.new_bytes, _cabi.POOL.reused_bytes)
     t0 = time.perf_counter()
     res = ba.bundle_adjust(fl, fl.numCam, max_iter=a.steps + 1, ftol=0.0, xtol=0.0, gtol=0.0, **BA_KW)
     torch.cuda.synchronize()
@@ -258,7 +259,8 @@ def main():
             'resid_jac_mdet_per_s': N_total / (ms[1] / 1e3) / 1e6,
             'roofline': roof, 'phases': phases, 'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'seconds': dt_e2e, 'steps': e2e_steps, 'host_phases_ms': res.stats.get('host')},
+                    'seconds': dt_e2e, 'steps': e2e_steps, 'host_phases_ms': res.stats.get('host'),
+                    'pinned_new_bytes': _cabi.POOL.new_bytes - pool0[0], 'pinned_reused_bytes': _cabi.POOL.reused_bytes - pool0[1]},
             'gpu_launches': int(st.launches), 'linear_solves': int(st.lm_iterations), 'final_cost': st.cost, 'cost0': st.cost0,
             'workload_gen_s': t_gen}
     if world == 1 and not a.no_cpu_baseline:

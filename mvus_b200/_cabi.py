@@ -98,6 +98,8 @@ class PinnedPool:
     def __init__(self):
         self.free = []          # (nbytes, ptr)
         self.total = 0
+        self.new_bytes = 0      # bytes newly pinned (diagnostic)
+        self.reused_bytes = 0
 
     def empty(self, n, dtype=np.float64):
         import weakref
@@ -117,6 +119,9 @@ class PinnedPool:
                 return np.empty(int(n), dtype=dtype)
             cap = nbytes
             self.total += nbytes
+            self.new_bytes += nbytes
+        else:
+            self.reused_bytes += nbytes
         buf = (ctypes.c_char * cap).from_address(ptr)
         arr = np.frombuffer(buf, dtype=dtype, count=int(n))
         weakref.finalize(buf, self.free.append, (cap, ptr))

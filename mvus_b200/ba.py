@@ -185,6 +185,8 @@ def _all_detect_to_traj(scene, fp, hd, x):
     in-interval detections with their spline positions) from the device (mvus_ba_global_traj)."""
     cams = fp.seq
     N = fp.N
+    # drop the previous call's arrays first so that their pinned blocks are reused
+    scene.global_detections = scene.frame_id_all = scene.global_time_stamps_all = scene.global_traj = None
     gd = _cabi.POOL.empty(3 * N).reshape(3, N)
     for k, i in enumerate(cams):
         a, b = fp.cam_ptr[k], fp.cam_ptr[k + 1]
@@ -227,9 +229,12 @@ def bundle_adjust(scene, numCam, max_iter=10, rs=False, motion_prior=False, moti
         """detections_global of the optimised cameras from the BA handle itself (one upload of
         the detections serves visibility, solve and refresh); cameras outside sequence[:numCam]
         go through a second, small handle."""
-        new = hd.detections_global(x)
         dg = list(scene.detections_global) if len(scene.detections_global) == scene.numCam \
             else [[] for _ in range(scene.numCam)]
+        for i in fp.seq:                    # drop the stale arrays first: their pinned block is reused
+            dg[i] = None
+        scene.detections_global = dg
+        new = hd.detections_global(x)
         for k, i in enumerate(fp.seq):
             dg[i] = new[k]
         scene.detections_global = dg
@@ -254,6 +259,7 @@ def bundle_adjust(scene, numCam, max_iter=10, rs=False, motion_prior=False, moti
     try:
         if _COMM is not None and _COMM[0] > 1:
             hd.comm_init(*_COMM)
+        scene.visible = None                # (stale array dropped first: pinned block reuse)
         visibility(hd, fp.x0)               # common.py:493
         lap('visibility_ms')
         x, r, st = hd.solve(fp.x0)

@@ -14,6 +14,11 @@ namespace mvus {
 
 constexpr int TILE_DET = 128;      // detections per CTA tile (one camera per tile)
 
+// Device buffer on the stream-ordered allocator.  The device's default memory pool is told to
+// keep freed memory (release threshold = max, set in mvus_ba_create), so the ~35 GB a config-4
+// handle needs are cudaMalloc'ed once per process and re-used by every later BA call (the
+// reference's main.py makes two BA calls per camera); plain cudaMalloc/cudaFree of that much memory
+// costs several hundred ms per call.
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -22,11 +27,18 @@ struct DevBuf {
         if (count <= n && p) return cudaSuccess;
         release();
         if (count == 0) return cudaSuccess;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), cudaStreamPerThread);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);   // usable on any stream afterwards
         if (e == cudaSuccess) n = count; else p = nullptr;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() {
+        if (p) {
+            cudaDeviceSynchronize();                 // nothing on any stream may still use it
+            cudaFreeAsync(p, cudaStreamPerThread);
+        }
+        p = nullptr; n = 0;
+    }
     size_t bytes() const { return n * sizeof(T); }
 };
 

@@ -45,6 +45,14 @@ extern "C" int mvus_ba_create(const mvus_ba_desc* desc, mvus_ba_handle* out) {
     if (desc->device < 0 || desc->device >= ndev) { g_create_err = "bad device ordinal"; return MVUS_ERR_ARG; }
     e = cudaSetDevice(desc->device);
     if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); return MVUS_ERR_CUDA; }
+    {   // keep freed device memory in the pool for the next handle (see DevBuf)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, desc->device) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        cudaGetLastError();
+    }
     mvus_ba_ctx* h = new mvus_ba_ctx();
     h->desc = *desc;
     h->nc = desc->num_cams;
