@@ -41,10 +41,14 @@ def parse():
     ap.add_argument('--sample-cams', type=int, default=4)
     ap.add_argument('--sample-det', type=int, default=1500)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='cfg4', choices=['cfg4', 'cfg2', 'cfg3', 'cfg5'],
+                    help='BASELINE.json config: cfg4 (default, the one the metric is quoted on), cfg2 7x100k RS+F, '
+                         'cfg3 = cfg2 + opt_calib + KE, cfg5 = batch of independent 7-camera problems')
+    ap.add_argument('--problems', type=int, default=1024, help='cfg5: number of independent problems')
     return ap.parse_args()
 
 
-def make_workload(cams, det, coef):
+def make_workload(cams, det, coef, opt_calib=False, motion_type='F', frames_per_knot=None):
     from concurrent.futures import ThreadPoolExecutor
     from mvus_b200 import synth
     # simulate cameras in parallel threads (NumPy releases the GIL in the heavy ufuncs)
@@ -61,8 +65,10 @@ def make_workload(cams, det, coef):
         return fut
     synth.simulate_detections = deferred
     try:
-        fl, truth = synth.make_flight(nc=cams, det_per_cam=det, n_coef=coef, rolling_shutter=True,
-                                      distortion=True, motion_type='F', motion_weights=1e4, uncovered=0.0)
+        fl, truth = synth.make_flight(nc=cams, det_per_cam=det, n_coef=None if frames_per_knot else coef,
+                                      frames_per_knot=frames_per_knot or 15.0, rolling_shutter=True,
+                                      distortion=True, opt_calib=opt_calib, motion_type=motion_type,
+                                      motion_weights=1e4, uncovered=0.0)
     finally:
         synth.simulate_detections = orig
     fl.detections = [f.result() for f in fl.detections]
@@ -71,6 +77,10 @@ def make_workload(cams, det, coef):
 
 
 def workload_name(a):
+    if a.workload == 'cfg2':
+        return 'cfg2: synthetic 7-camera x 100000-detection flight, 15 frames/knot, rolling shutter + motion F (w=1e4)'
+    if a.workload == 'cfg3':
+        return 'cfg3: cfg2 with opt_calib (15 camera unknowns) and motion KE (w=1e2)'
     return ('synthetic %d-camera x %d-detection flight, %d spline coefficients/axis, rolling shutter + '
             'motion F (w=1e4), fixed calibration' % (a.cams, a.det, a.coef))
 
@@ -138,11 +148,67 @@ def cpu_reference_run(a, steps, warmup):
     return val, info, dt, iters
 
 
+def run_cfg5(a, rank, world, local):
+    """Batch of independent problems (BASELINE config 5), partitioned across ranks."""
+    import torch
+    import torch.distributed as dist
+    from mvus_b200 import ba, batch, synth
+    torch.cuda.set_device(local)
+    ba.DEVICE = local
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    mine = batch.my_problems(a.problems, rank, world)
+    scenes = {p: synth.make_flight(nc=7, det_per_cam=5000, seed=7 * p, rolling_shutter=True, distortion=True,
+                                   motion_type='F', motion_weights=1e4, uncovered=0.0)[0] for p in mine}
+    ndet = sum(sum(d.shape[1] for d in s.detections) for s in scenes.values())
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        for p in mine[:2]:                                            # warm-up on copies of two problems
+            synth.make_flight(nc=7, det_per_cam=5000, seed=7 * p, rolling_shutter=True, distortion=True,
+                              motion_type='F', motion_weights=1e4, uncovered=0.0)[0].BA(7, max_iter=a.steps + 1, **BA_KW)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = {p: scenes[p].BA(7, max_iter=a.steps + 1, **BA_KW) for p in mine}
+        torch.cuda.synchronize()
+    tot = torch.tensor([time.perf_counter() - t0, float(ndet), float(sum(r.nfev - 1 for r in res.values())),
+                        sum(r.stats['ms_total'] for r in res.values()), float(sum(r.stats['launches'] for r in res.values()))],
+                       dtype=torch.float64, device='cuda')
+    mx = tot.clone()
+    if world > 1:
+        dist.all_reduce(tot)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    tot, mx = tot.cpu().tolist(), mx.cpu().tolist()
+    if rank == 0:
+        steps = tot[2] / a.problems
+        line = {'metric': METRIC, 'value': tot[1] * steps / mx[0] / 1e6, 'unit': UNIT, 'n_gpus': world,
+                'steps': steps, 'warmup': 2, 'ms_per_step': mx[0] * 1e3 / max(steps, 1) / (a.problems / world),
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': 'cfg5: %d independent 7-camera x 5000-detection problems, RS + motion F, '
+                                       'partitioned round-robin over %d GPU(s); end-to-end Scene.BA calls' % (a.problems, world)},
+                'problems_per_s': a.problems / mx[0], 'device_ms_sum_max_rank': mx[3], 'gpu_launches': int(tot[4]),
+                'e2e': {'value': tot[1] * steps / mx[0] / 1e6, 'unit': UNIT, 'seconds': mx[0]}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    global BA_KW
+    wl_kw = {}
+    if a.workload in ('cfg2', 'cfg3'):
+        a.cams, a.det, a.coef = 7, 100000, 0
+        wl_kw = dict(frames_per_knot=15.0)
+        if a.workload == 'cfg3':
+            wl_kw.update(opt_calib=True, motion_type='KE')
+            BA_KW = dict(rs=True, motion_reg=True, motion_weights=1e2)
+    if a.workload == 'cfg5' and a.impl == 'ours':
+        return run_cfg5(a, rank, world, local)
     cfg = {'workload': workload_name(a), 'cams': a.cams, 'det_per_cam': a.det, 'coef_per_axis': a.coef,
            'l2_policy': 'inputs (J planes >= 0.3 GB) exceed L2; no flush needed',
            'parallelism': 'detections sharded by camera+time chunk over %d GPU(s), NCCL all-reduce of normal equations' % world}
@@ -171,7 +237,7 @@ def main():
         shard.init_comm()
 
     t0 = time.perf_counter()
-    fl = make_workload(a.cams, a.det, a.coef)
+    fl = make_workload(a.cams, a.det, a.coef, **wl_kw)
     t_gen = time.perf_counter() - t0
     N_total = int(sum(d.shape[1] for d in fl.detections))
     if world > 1:

@@ -276,3 +276,19 @@ def test_full_size_cfg2_recovers_ground_truth(built_lib):
     err = np.sqrt(np.sum((Pa - Q) ** 2, axis=0))
     assert np.sqrt(np.mean(err[:fl.numCam] ** 2)) < 0.02
     assert np.sqrt(np.mean(err[fl.numCam:] ** 2)) < 0.02
+
+
+def test_batch_of_independent_problems(built_lib):
+    """Config 5 shape (reduced count): independent 7-camera problems through Scene.BA, each checked
+    against the oracle's cost at the returned parameters."""
+    from mvus_b200 import batch, synth
+    scenes = [synth.make_flight(nc=7, det_per_cam=1500, seed=10 * k, rolling_shutter=True, distortion=True,
+                                motion_type='F', motion_weights=1e2)[0] for k in range(4)]
+    bakw = dict(rs=True, motion_reg=True, motion_weights=1e2)
+    res = batch.solve_many(scenes, max_iter=10, **bakw)
+    assert sorted(res) == [0, 1, 2, 3]
+    for p, sc in enumerate(scenes):
+        prob = ba_oracle.Problem(sc, sc.numCam, **bakw)
+        assert abs(prob.cost(prob.x0) - res[p].cost) <= 1e-9 * res[p].cost
+        assert res[p].cost < res[p].stats['cost0']
+    assert np.all(batch.gather_costs(res, 4) > 0)

@@ -83,3 +83,13 @@ def test_shard_scene_keeps_every_camera():
         assert (cat == fl.detections[i]).all()
         assert all(p.detections[i].shape[1] > 0 for p in parts)
     assert parts[0].spline['tck'][0][1][0] is fl.spline['tck'][0][1][0] or True
+
+
+def test_batch_partition_covers_every_problem_once():
+    from mvus_b200 import batch
+    for n in (0, 1, 7, 1024):
+        for w in (1, 2, 8):
+            owned = [batch.my_problems(n, r, w) for r in range(w)]
+            flat = sorted(i for o in owned for i in o)
+            assert flat == list(range(n))
+            assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
