@@ -295,7 +295,7 @@ __global__ void floor_kernel(double* __restrict__ v, int64_t n, const double* __
 //   - if j is an odd multiple of s (or the root pass): factor D_j, form ZL/ZR/W~ rows.
 // ZR is stored in E[j]; root = final pass on block 0.
 template <int Q>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(256, 2)
 bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* __restrict__ Dw,
                  double* __restrict__ Ew, double* __restrict__ Ww, double* __restrict__ ZL,
                  int* __restrict__ fail_flag) {
@@ -399,14 +399,14 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* _
 #pragma unroll
         for (int a = 0; a < Q; ++a) w[a] = Wj[(int64_t)a * ldw + c];
         if (has_m)
-#pragma unroll 1
+#pragma unroll 3
             for (int k = 0; k < Q; ++k) {
                 const double x = Wm[(int64_t)k * ldw + c];
 #pragma unroll
                 for (int a = 0; a < Q; ++a) w[a] -= zr_m[k * Q + a] * x;
             }
         if (has_p)
-#pragma unroll 1
+#pragma unroll 3
             for (int k = 0; k < Q; ++k) {
                 const double x = Wp[(int64_t)k * ldw + c];
 #pragma unroll
@@ -952,7 +952,8 @@ struct BcrView {          // a block-tridiagonal system (possibly a sub-range of
 };
 
 inline void launch_level(mvus_ba_ctx* h, const BcrView& v, int grid, int64_t s, int64_t sp, int root, int* fail_flag) {
-#define MV_LVL(QQ) bcr_level_kernel<QQ><<<grid, 128, 0, h->st>>>(v.nb, h->ldw, s, sp, root, v.Dw, v.Ew, v.Ww, v.ZL, fail_flag)
+    const int nthr = h->ldw > 192 ? 256 : 128;      // one W~ column per thread and pass
+#define MV_LVL(QQ) bcr_level_kernel<QQ><<<grid, nthr, 0, h->st>>>(v.nb, h->ldw, s, sp, root, v.Dw, v.Ew, v.Ww, v.ZL, fail_flag)
     switch (h->q) {
         case 9: MV_LVL(9); break;
         case 12: MV_LVL(12); break;
