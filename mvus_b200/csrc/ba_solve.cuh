@@ -462,6 +462,9 @@ syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int slab, double*
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    // warp tiles that only hold padding columns (last tile: ldw = 577 of 640) or lie strictly above
+    // the diagonal of a diagonal tile pair contribute nothing: they still stage data, but skip the MMAs
+    const bool warp_active = (ti * SY_T + wy * 32 < ldw) && (tj * SY_T + wx * 32 < ldw) && !(diag && wx > wy);
     // each thread stages 4 elements of each panel per chunk: idx = tid + 512*k -> (row, col)
     double pa[4], pb[4];
     auto gload = [&](int64_t rr) {
@@ -491,6 +494,7 @@ syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int slab, double*
         __syncthreads();
         if (rr + SY_K < r1) gload(rr + SY_K);
         const double (*Bp)[SY_LD] = diag ? As : Bs;
+        if (warp_active)
 #pragma unroll
         for (int ks = 0; ks < SY_K; ks += 4) {
             double a[4], b[4];
