@@ -38,13 +38,18 @@ struct K2Cfg {
     static constexpr int THREADS = 256;
     static constexpr int EPT = (NE + THREADS - 1) / THREADS;
     static constexpr int LDT = TILE_DET + 1;
-    // J planes + span + run table (start, g, 4 x (kb, loc))
+    // J planes + span + run table (start, g, 4 x (block, row))
     static constexpr size_t SMEM = (size_t)(2 * (P + 1)) * LDT * sizeof(double) +
                                    (size_t)(TILE_DET + (TILE_DET + 1) + TILE_DET + 8 * TILE_DET + 8) * sizeof(int);
 };
 
 enum { K2_NONE = 0, K2_CAMCAM, K2_CAMRES, K2_CAMCTRL, K2_CTRLCTRL, K2_CTRLRES };
 
+// v2b: same mapping as v2 (thread e owns entry (a, b) of the per-detection outer product, all
+// warps work on the same run) with the per-run flush reduced to a few instructions: everything
+// that depends only on the thread's entry (type, slots, axes, camera column) is computed once, and
+// the run table carries, per run and slot, the super-block and the global row (kb*q + 3*local) of
+// the control point, so a flush is 1-2 shared loads, one 64-bit multiply-add and the RED.
 template <int P>
 __global__ void __launch_bounds__(256)
 accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, const int* __restrict__ span,
@@ -53,42 +58,46 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
                   int Pc, int bw, int ldw, double* __restrict__ A, double* __restrict__ bc,
                   double* __restrict__ D, double* __restrict__ E, double* __restrict__ W) {
     using Cfg = K2Cfg<P>;
+    constexpr int LDT = Cfg::LDT;
     extern __shared__ double s_mem[];
     double* s_J = s_mem;                                        // [2*(P+1)][LDT]
-    int* s_span = reinterpret_cast<int*>(s_mem + (size_t)2 * (P + 1) * Cfg::LDT);
+    int* s_span = reinterpret_cast<int*>(s_mem + (size_t)2 * (P + 1) * LDT);
     int* s_rstart = s_span + TILE_DET;                          // [TILE_DET + 1]
     int* s_rg = s_rstart + TILE_DET + 1;                        // [TILE_DET]
-    int* s_kb = s_rg + TILE_DET;                                // [TILE_DET][4]
-    int* s_loc = s_kb + 4 * TILE_DET;                           // [TILE_DET][4]
-    int* s_misc = s_loc + 4 * TILE_DET;                         // [0] = number of runs, [1..4] warp counts
+    int* s_kb = s_rg + TILE_DET;                                // [TILE_DET][4] super-block of slot m (-1: none)
+    int* s_row = s_kb + 4 * TILE_DET;                           // [TILE_DET][4] global row kb*q + 3*local
+    int* s_misc = s_row + 4 * TILE_DET;                         // [0] = number of runs, [1..4] warp counts
     const int tl = blockIdx.x, cam = tile_cam[tl], cnt = tile_cnt[tl];
     const int64_t d0 = tile_start[tl];
     const int q = 3 * bw;
     const int tid = threadIdx.x;
-    // stage: planes 0..P-1 = u row, P = r_u, P+1..2P = v row, 2P+1 = r_v
-    for (int idx = tid; idx < 2 * (P + 1) * TILE_DET; idx += blockDim.x) {
-        const int pl = idx / TILE_DET, t = idx - pl * TILE_DET;
-        double v = 0.0;
-        if (t < cnt) {
-            const int half = pl / (P + 1), p = pl - half * (P + 1);
-            if (p < P) v = __ldcs(J + (int64_t)(half * P + p) * N + d0 + t);
-            else {
-                const int64_t r0 = row_off[cam], ncam = (row_off[cam + 1] - r0) >> 1;
-                v = r[r0 + half * ncam + (d0 + t - (r0 >> 1))];
+    // ---- stage: planes 0..P-1 = u row, P = r_u, P+1..2P = v row, 2P+1 = r_v (coalesced plane reads)
+    {
+        const int t = tid & (TILE_DET - 1), p0 = tid >> 7;
+        const bool in = t < cnt;
+        const int64_t r0 = row_off[cam], ncam = (row_off[cam + 1] - r0) >> 1;
+        const int64_t loc = d0 + t - (r0 >> 1);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const double* src = J + (int64_t)(half * P + p0) * N + d0 + t;
+            double* dst = s_J + (half * (P + 1) + p0) * LDT + t;
+#pragma unroll 6
+            for (int p = p0; p < P; p += 2) {
+                *dst = in ? __ldcs(src) : 0.0;
+                src += 2 * N;
+                dst += 2 * LDT;
             }
+            if (p0 == (P & 1)) s_J[(half * (P + 1) + P) * LDT + t] = in ? r[r0 + half * ncam + loc] : 0.0;
         }
-        s_J[pl * Cfg::LDT + t] = v;
     }
     if (tid < TILE_DET) s_span[tid] = tid < cnt ? span[d0 + tid] : -2;
     __syncthreads();
-    // run table: maximal runs of equal span index (ballot scan over the 128 tile slots)
+    // ---- run table: maximal runs of equal span index (ballot scan over the 128 tile slots)
     if (tid < TILE_DET) {
         const int g = s_span[tid];
         const bool head = tid < cnt && (tid == 0 || g != s_span[tid - 1]);
         const unsigned bal = __ballot_sync(0xffffffffu, head);
         if ((tid & 31) == 0) s_misc[1 + (tid >> 5)] = __popc(bal);
-        __syncwarp();
-        // the 4 warps of this branch synchronise through the barrier below; compute prefix later
         s_rg[tid] = head ? (int)(__popc(bal & ((1u << (tid & 31)) - 1u))) : -1;   // rank inside the warp
     }
     __syncthreads();
@@ -100,10 +109,8 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
         __syncwarp();
         if (tid == 0) s_misc[0] = s_misc[1] + s_misc[2] + s_misc[3] + s_misc[4];
         if (rk >= 0) {
-            const int ridx = base + rk;
-            s_rstart[ridx] = tid;
-            // overwrite s_rg lazily below (needs all ranks read first)
-            s_kb[ridx * 4] = g;            // stash g; expanded after the barrier
+            s_rstart[base + rk] = tid;
+            s_kb[(base + rk) * 4] = g;     // stash g; expanded after the barrier
         }
     }
     __syncthreads();
@@ -115,72 +122,77 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int j = g - 3 + m;
-            int kb = -1, loc = 0;
-            if (g >= 0 && j >= 0) { kb = j / bw; loc = (j - kb * bw) * 3; }
+            int kb = -1, row = 0;
+            if (g >= 0 && j >= 0) { kb = j / bw; row = kb * q + (j - kb * bw) * 3; }
             s_kb[tid * 4 + m] = kb;
-            s_loc[tid * 4 + m] = loc;
+            s_row[tid * 4 + m] = row;
         }
     }
     __syncthreads();
 
-    int typ[Cfg::EPT], ia[Cfg::EPT], ib[Cfg::EPT];
+    // ---- per-thread entry constants
+    int typ[Cfg::EPT], sa[Cfg::EPT], sb[Cfg::EPT], xa[Cfg::EPT], xb[Cfg::EPT];
     const double* pa[Cfg::EPT];
     const double* pb[Cfg::EPT];
-    double acc[Cfg::EPT], cacc[Cfg::EPT];
+    double cacc[Cfg::EPT];
 #pragma unroll
     for (int k = 0; k < Cfg::EPT; ++k) {
         int e = tid + k * Cfg::THREADS;
-        typ[k] = K2_NONE; ia[k] = 0; ib[k] = 0; acc[k] = 0.0; cacc[k] = 0.0;
+        typ[k] = K2_NONE; sa[k] = 0; sb[k] = 0; xa[k] = 0; xb[k] = 0; cacc[k] = 0.0;
         pa[k] = s_J; pb[k] = s_J;
         if (e < Cfg::NE) {
             int a = 0;
             while (e >= (P + 1 - a)) { e -= (P + 1 - a); ++a; }
             const int b = a + e;
-            pa[k] = s_J + a * Cfg::LDT; pb[k] = s_J + b * Cfg::LDT;
-            ia[k] = a; ib[k] = b;
-            if (a < Pc) typ[k] = b < Pc ? K2_CAMCAM : (b == P ? K2_CAMRES : K2_CAMCTRL);
-            else if (a < P) typ[k] = b == P ? K2_CTRLRES : K2_CTRLCTRL;
+            pa[k] = s_J + a * LDT; pb[k] = s_J + b * LDT;
+            if (a < Pc) {
+                if (b < Pc) { typ[k] = K2_CAMCAM; xa[k] = a; xb[k] = b; }
+                else if (b == P) { typ[k] = K2_CAMRES; xa[k] = a; }
+                else { typ[k] = K2_CAMCTRL; sb[k] = (b - Pc) / 3; xb[k] = (b - Pc) - 3 * sb[k]; xa[k] = cam * Pc + a; }
+            } else if (a < P) {
+                sa[k] = (a - Pc) / 3; xa[k] = (a - Pc) - 3 * sa[k];
+                if (b == P) typ[k] = K2_CTRLRES;
+                else { typ[k] = K2_CTRLCTRL; sb[k] = (b - Pc) / 3; xb[k] = (b - Pc) - 3 * sb[k]; }
+            }
         }
     }
-    constexpr int VOFF = (P + 1) * Cfg::LDT;
+    constexpr int VOFF = (P + 1) * LDT;
     for (int rr = 0; rr < nruns; ++rr) {
-        const int t0 = s_rstart[rr], t1 = s_rstart[rr + 1];
         if (s_rg[rr] < 0) continue;              // uncovered detections: zero rows
+        const int t0 = s_rstart[rr], t1 = s_rstart[rr + 1];
 #pragma unroll
         for (int k = 0; k < Cfg::EPT; ++k) {
             double s = 0.0;
-            const double* qa = pa[k];
-            const double* qb = pb[k];
-            for (int t = t0; t < t1; ++t) s = fma(qa[t], qb[t], fma(qa[VOFF + t], qb[VOFF + t], s));
-            acc[k] = s;
-        }
-        // flush control-point entries of this run
-#pragma unroll
-        for (int k = 0; k < Cfg::EPT; ++k) {
+            const double* qa = pa[k] + t0;
+            const double* qb = pb[k] + t0;
+            int n = t1 - t0;
+#pragma unroll 1
+            for (; n >= 4; n -= 4, qa += 4, qb += 4) {
+                s = fma(qa[0], qb[0], fma(qa[VOFF], qb[VOFF], s));
+                s = fma(qa[1], qb[1], fma(qa[VOFF + 1], qb[VOFF + 1], s));
+                s = fma(qa[2], qb[2], fma(qa[VOFF + 2], qb[VOFF + 2], s));
+                s = fma(qa[3], qb[3], fma(qa[VOFF + 3], qb[VOFF + 3], s));
+            }
+#pragma unroll 1
+            for (; n > 0; --n, ++qa, ++qb) s = fma(qa[0], qb[0], fma(qa[VOFF], qb[VOFF], s));
             const int ty = typ[k];
-            const double v = acc[k];
-            if (ty <= K2_CAMRES) { cacc[k] += v; continue; }
-            if (v == 0.0) continue;
-            const int a = ia[k], b = ib[k];
+            if (ty <= K2_CAMRES) { cacc[k] += s; continue; }
+            if (s == 0.0) continue;
+            const int kbb = s_kb[rr * 4 + sb[k]];
             if (ty == K2_CAMCTRL) {
-                const int mb = (b - Pc) / 3, bx = (b - Pc) - mb * 3;
-                const int kb = s_kb[rr * 4 + mb];
-                if (kb >= 0) atomicAdd(W + ((int64_t)kb * q + s_loc[rr * 4 + mb] + bx) * ldw + cam * Pc + a, v);
-            } else if (ty == K2_CTRLRES) {
-                const int ma = (a - Pc) / 3, ax = (a - Pc) - ma * 3;
-                const int kb = s_kb[rr * 4 + ma];
-                if (kb >= 0) atomicAdd(W + ((int64_t)kb * q + s_loc[rr * 4 + ma] + ax) * ldw + (ldw - 1), -v);
+                if (kbb >= 0) atomicAdd(W + (int64_t)(s_row[rr * 4 + sb[k]] + xb[k]) * ldw + xa[k], s);
             } else {
-                const int ma = (a - Pc) / 3, ax = (a - Pc) - ma * 3;
-                const int mb = (b - Pc) / 3, bx = (b - Pc) - mb * 3;
-                const int kba = s_kb[rr * 4 + ma], kbb = s_kb[rr * 4 + mb];
-                if (kba < 0 || kbb < 0) continue;
-                const int la = s_loc[rr * 4 + ma] + ax, lb = s_loc[rr * 4 + mb] + bx;
+                const int kba = s_kb[rr * 4 + sa[k]];
+                if (kba < 0) continue;
+                const int ra = s_row[rr * 4 + sa[k]] + xa[k];
+                if (ty == K2_CTRLRES) { atomicAdd(W + (int64_t)ra * ldw + (ldw - 1), -s); continue; }
+                if (kbb < 0) continue;
+                const int rb = s_row[rr * 4 + sb[k]] + xb[k];
                 if (kba == kbb) {
-                    atomicAdd(D + ((int64_t)kba * q + la) * q + lb, v);
-                    if (la != lb) atomicAdd(D + ((int64_t)kba * q + lb) * q + la, v);
+                    atomicAdd(D + (int64_t)ra * q + (rb - kbb * q), s);
+                    if (ra != rb) atomicAdd(D + (int64_t)rb * q + (ra - kba * q), s);
                 } else {
-                    atomicAdd(E + ((int64_t)kba * q + la) * q + lb, v);
+                    atomicAdd(E + (int64_t)ra * q + (rb - kbb * q), s);
                 }
             }
         }
@@ -190,12 +202,11 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
     for (int k = 0; k < Cfg::EPT; ++k) {
         const double v = cacc[k];
         if (v == 0.0) continue;
-        const int a = ia[k], b = ib[k];
         if (typ[k] == K2_CAMCAM) {
-            atomicAdd(A + ((int64_t)cam * Pc + a) * Pc + b, v);
-            if (a != b) atomicAdd(A + ((int64_t)cam * Pc + b) * Pc + a, v);
+            atomicAdd(A + ((int64_t)cam * Pc + xa[k]) * Pc + xb[k], v);
+            if (xa[k] != xb[k]) atomicAdd(A + ((int64_t)cam * Pc + xb[k]) * Pc + xa[k], v);
         } else if (typ[k] == K2_CAMRES) {
-            atomicAdd(bc + cam * Pc + a, -v);
+            atomicAdd(bc + cam * Pc + xa[k], -v);
         }
     }
 }
