@@ -80,7 +80,7 @@ struct mvus_ba_ctx {
 
     // per-evaluation state
     mvus::DevBuf<double> x, x_trial, camprep, r, J, mJ, partial, scratch;
-    mvus::DevBuf<int> span, mbase, flag;
+    mvus::DevBuf<int> span, mbase, flag, frozen;
     double* h_pin = nullptr;      // pinned scratch for scalars
     size_t h_pin_n = 0;
 

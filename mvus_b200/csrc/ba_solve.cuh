@@ -534,10 +534,35 @@ syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int slab, double*
             }
 }
 
+// rs_bounds (common.py:655-660, scipy trf_bounds): active-set treatment of the box 0 <= rho <= 1.
+// A rho that sits on a bound while the descent direction -g pushes it outward is frozen for this
+// linear solve (its row/column leave the system); free ones are stepped and projected afterwards.
+__global__ void active_rho_kernel(const double* __restrict__ x, const double* __restrict__ bc, int nc, int Pc,
+                                  int rs_bounds, int* __restrict__ frozen) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nc * Pc) return;
+    int f = 0;
+    if (rs_bounds && (i % Pc) == 2) {
+        const int cam = i / Pc;
+        const double rho = x[2 * nc + cam], b = bc[i];        // b = -gradient
+        f = (rho <= 0.0 && b < 0.0) || (rho >= 1.0 && b > 0.0);
+    }
+    frozen[i] = f;
+}
+
+__global__ void freeze_cols_kernel(double* __restrict__ Ww, int64_t rows, int ldw, int nc, int Pc,
+                                   const int* __restrict__ frozen) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    for (int cam = 0; cam < nc; ++cam)
+        if (frozen[cam * Pc + 2]) Ww[row * ldw + cam * Pc + 2] = 0.0;
+}
+
 // S = blockdiag(A) + lam * diag - S~ (lower triangle), rhs = bc - S~[ncP][:]
 __global__ void form_schur_kernel(const double* __restrict__ A, const double* __restrict__ bc,
                                   const double* __restrict__ diag_c, double lam, int nc, int Pc, int ldw,
-                                  double* __restrict__ Sfull, double* __restrict__ rhs) {
+                                  const int* __restrict__ frozen, double* __restrict__ Sfull,
+                                  double* __restrict__ rhs) {
     const int ncP = nc * Pc;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)ncP * ncP) return;
@@ -548,8 +573,9 @@ __global__ void form_schur_kernel(const double* __restrict__ A, const double* __
     if (cr == cc) v += A[((int64_t)cr * Pc + (row - cr * Pc)) * Pc + (col - cc * Pc)];
     if (row == col) {
         v += lam * diag_c[row];
-        rhs[row] = bc[row] - Sfull[(int64_t)ncP * ldw + row];
+        rhs[row] = frozen[row] ? 0.0 : bc[row] - Sfull[(int64_t)ncP * ldw + row];
     }
+    if (frozen[row] || frozen[col]) v = (row == col) ? 1.0 : 0.0;
     Sfull[(int64_t)row * ldw + col] = v;
 }
 
@@ -893,6 +919,8 @@ inline int solver_alloc(mvus_ba_ctx* h) {
     MV_CUDA(h, h->dlt_c.alloc(h->ncP));
     MV_CUDA(h, h->dlt_s.alloc(((size_t)h->nb + 1) * h->q));
     MV_CUDA(h, h->diag_c.alloc(h->ncP));
+    MV_CUDA(h, h->frozen.alloc(h->ncP));
+    MV_CUDA(h, cudaMemsetAsync(h->frozen.p, 0, h->ncP * sizeof(int), h->st));
     MV_CUDA(h, h->diag_s.alloc((size_t)h->nb * h->q));
     MV_CUDA(h, h->bs.alloc(((size_t)h->nb + 1) * h->q));
     MV_CUDA(h, h->gvec.alloc(h->n));
@@ -1065,11 +1093,15 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
         MV_CUDA(h, cudaMemcpyAsync(h->Ew.p, h->E.p, nb * qq * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
         MV_CUDA(h, cudaMemcpyAsync(h->Ww.p, h->W.p, (size_t)nbq * ldw * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
         h->launches += 1;
+        if (h->desc.rs_bounds) {
+            freeze_cols_kernel<<<(int)((nbq + 255) / 256), 256, 0, h->st>>>(h->Ww.p, nbq, ldw, h->nc, h->Pc, h->frozen.p);
+            h->launches++;
+        }
         BcrView v{h->Dw.p, h->Ew.p, h->Ww.p, h->ZL.p, h->dlt_s.p, nb};
         std::vector<int64_t> levels = bcr_eliminate(h, v, nb, true, fail_flag);
         launch_syrk(h, h->Ww.p, nbq, h->Sd.p);
         form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
-            h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->Sd.p, rhs);
+            h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->frozen.p, h->Sd.p, rhs);
         h->launches++;
         dense_chol_solve(h, h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
         wdc_kernel<<<(int)((nbq * 32 + 255) / 256), 256, 0, h->st>>>(h->Ww.p, h->dlt_c.p, nbq, ldw, h->dlt_s.p);
@@ -1092,6 +1124,10 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
             MV_CUDA(h, cudaMemcpyAsync(h->Ew.p + lo * qq, h->E.p + lo * qq, nloc * qq * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
             MV_CUDA(h, cudaMemcpyAsync(h->Ww.p + lo * wn, h->W.p + lo * wn, (size_t)nloc * wn * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
             h->launches++;
+            if (h->desc.rs_bounds) {
+                freeze_cols_kernel<<<(int)((nloc * q + 255) / 256), 256, 0, h->st>>>(h->Ww.p + lo * wn, nloc * q, ldw, h->nc, h->Pc, h->frozen.p);
+                h->launches++;
+            }
         }
         MV_CUDA(h, cudaMemsetAsync(h->Dw.p + hi * qq, 0, qq * sizeof(double), h->st));
         MV_CUDA(h, cudaMemsetAsync(h->Ew.p + hi * qq, 0, qq * sizeof(double), h->st));
@@ -1122,7 +1158,7 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
         e = nccl_sum(h, h->Sd.p, (size_t)ldw * ldw);
         if (e) return e;
         form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
-            h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->Sd.p, rhs);
+            h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->frozen.p, h->Sd.p, rhs);
         h->launches++;
         dense_chol_solve(h, h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
         e = nccl_bcast0(h, h->dlt_c.p, (size_t)h->ncP);

@@ -83,7 +83,7 @@ extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
         b->release();
     for (auto* b : {&h->row_off, &h->tile_start, &h->knot_off, &h->ctrl_off, &h->xoff, &h->lut_off}) b->release();
     for (auto* b : {&h->tile_cam, &h->tile_cnt, &h->ncoef, &h->deg, &h->lut_n, &h->lut, &h->tau_spl, &h->span,
-                    &h->mbase, &h->flag})
+                    &h->mbase, &h->flag, &h->frozen})
         b->release();
     h->tau_flag.release();
     if (h->h_pin) cudaFreeHost(h->h_pin);
@@ -476,6 +476,11 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
             rc = accumulate(h);
             if (!rc) rc = reduce_normal_equations(h, false);
             if (!rc) rc = compute_diag(h);
+            if (!rc && h->desc.rs_bounds) {
+                active_rho_kernel<<<(h->ncP + 127) / 128, 128, 0, h->st>>>(
+                    h->x.p, h->A.p + (size_t)h->nc * h->Pc * h->Pc, h->nc, h->Pc, 1, h->frozen.p);
+                h->launches++;
+            }
             t.stop();
             if (rc) return rc;
             need_accum = false;

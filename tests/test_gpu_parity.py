@@ -292,3 +292,91 @@ def test_batch_of_independent_problems(built_lib):
         assert abs(prob.cost(prob.x0) - res[p].cost) <= 1e-9 * res[p].cost
         assert res[p].cost < res[p].stats['cost0']
     assert np.all(batch.gather_costs(res, 4) > 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: empty / ragged inputs, all-uncovered cameras, unsupported knot density, satellites
+def test_ragged_and_empty_cameras(built_lib):
+    """A camera with zero detections, one with a single detection and one whose detections all
+    fall outside every spline interval: residual/Jacobian parity and a working solve."""
+    fl, truth, bakw = cases.make('rs_F_gap')
+    fl.detections[1] = fl.detections[1][:, :0]                      # empty
+    fl.detections[2] = fl.detections[2][:, 5:6]                     # one detection
+    d3 = fl.detections[3].copy()
+    d3[0] += 1e6                                                    # far beyond the last interval
+    fl.detections[3] = d3
+    fp = FlatProblem(fl, fl.numCam, **bakw)
+    prob = ba_oracle.Problem(fl, fl.numCam, **bakw)
+    hd = _cabi.Handle(fp, max_nfev=6)
+    r, span, J, mbase, mJ = hd.residual_jacobian(fp.x0)
+    ro = prob.residual(prob.x0)
+    assert np.abs(r - ro).max() <= RTOL * max(1.0, np.abs(ro).max())
+    assert (span[fp.cam_ptr[3]:fp.cam_ptr[4]] == -1).all()
+    Jg = helpers.expand_jacobian(fp, span, J, mbase, mJ)
+    import scipy.sparse as sp
+    Jo = prob.jacobian(prob.x0).tocsc() @ sp.diags(prob.free_mask().astype(float))
+    colmax = np.maximum(abs(Jo).max(axis=0).toarray().ravel(), 1e-300)
+    assert (abs(Jg - Jo).tocsc().max(axis=0).toarray().ravel() / colmax).max() <= RTOL
+    x, rr, st = hd.solve(fp.x0)
+    assert np.isfinite(st.cost) and st.cost < st.cost0
+    assert abs(prob.cost(x) - st.cost) <= 1e-9 * st.cost
+    hd.close()
+
+
+def test_unsupported_knot_density_fails_loudly(built_lib):
+    """Knots denser than the unit motion grid make a motion row touch > 7 control points: the
+    library must refuse (MVUS_ERR_UNSUPPORTED), never silently truncate the row."""
+    fl, truth, bakw = cases.make('rs_F_gap', frames_per_knot=0.4, det_per_cam=120, gaps=())
+    fp = FlatProblem(fl, fl.numCam, **bakw)
+    hd = _cabi.Handle(fp, max_nfev=3)
+    with pytest.raises(_cabi.MvusError, match='7 consecutive control points'):
+        hd.solve(fp.x0)
+    hd.close()
+
+
+def test_non_finite_start_raises_like_scipy(built_lib):
+    fl, truth, bakw = cases.make('gs_plain')
+    fp = FlatProblem(fl, fl.numCam, **bakw)
+    hd = _cabi.Handle(fp)
+    x0 = fp.x0.copy()
+    x0[fp.n_other + 5] = np.nan
+    with pytest.raises(ValueError, match='Residuals are not finite in the initial point'):
+        hd.solve(x0)
+    hd.close()
+
+
+def test_error_cam_and_remove_outliers(built_lib):
+    """Scene.error_cam (common.py:304-359) in all four modes and Scene.remove_outliers
+    (common.py:700-717) through the residual kernel, against the oracle."""
+    fl, truth, bakw = cases.make('rs_F_gap')
+    prob = ba_oracle.Problem(fl, fl.numCam, rs=True)
+    ro = prob.residual(prob.x0)
+    for i in range(fl.numCam):
+        N = fl.detections[i].shape[1]
+        eu, ev = ro[prob.row_off[i]:prob.row_off[i] + N], ro[prob.row_off[i] + N:prob.row_off[i] + 2 * N]
+        cov = prob._cam_terms(prob.x0, i)['idx'] > 0
+        each = fl.error_cam(i, mode='each')
+        assert np.abs(each - np.concatenate((eu, ev))).max() <= 1e-9 * max(1.0, each.max())
+        dist = fl.error_cam(i)
+        assert np.abs(dist - np.sqrt(eu[cov] ** 2 + ev[cov] ** 2)).max() <= 1e-9 * max(1.0, dist.max())
+        assert fl.error_cam(i, mode='xy_2D').shape == (2, cov.sum())
+        assert fl.error_cam(i, mode='xy_1D').shape == (2 * cov.sum(),)
+    n_before = [d.shape[1] for d in fl.detections]
+    thres = 8.0
+    keep = []
+    for i in range(fl.numCam):
+        N = n_before[i]
+        eu, ev = ro[prob.row_off[i]:prob.row_off[i] + N], ro[prob.row_off[i] + N:prob.row_off[i] + 2 * N]
+        keep.append(np.sqrt(eu ** 2 + ev ** 2) < thres)
+    fl.remove_outliers(range(fl.numCam), thres=thres)
+    for i in range(fl.numCam):
+        assert fl.detections[i].shape[1] == keep[i].sum() < n_before[i]
+        assert fl.detections_global[i].shape == (3, keep[i].sum())
+
+
+def test_rs_bounds_keep_rho_in_box(built_lib):
+    """BA(rs_bounds=True): rho stays in [0, 1] (common.py:655-660) and the cost still decreases."""
+    fl, truth, bakw = cases.make('rs_bounds_dense', init_rs=[0.0, 1.0, 0.02])
+    res = fl.BA(fl.numCam, max_iter=15, **bakw)
+    assert (fl.rs >= 0.0).all() and (fl.rs <= 1.0).all()
+    assert res.cost < res.stats['cost0']

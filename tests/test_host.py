@@ -99,3 +99,33 @@ def test_solver_model_matches_dense_solve():
         ok = perm >= 0
         mine[perm[ok]] = flat[ok]
         assert np.abs(mine - ref).max() <= 1e-8 * np.abs(ref).max()
+
+
+def test_dropin_installs_on_the_reference_module():
+    """mvus_b200.dropin.install replaces Scene.BA (and the error_cam / remove_outliers satellites)
+    of the UNMODIFIED reference module with the same signatures."""
+    import inspect
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip('reference tree not present (GPU box)')
+    from mvus_b200 import dropin
+    common = ref_shim.load()
+    sig_before = inspect.signature(common.Scene.BA)
+    orig = dropin.install(common)
+    try:
+        assert common.Scene.BA is not orig and common.Scene._reference_BA is orig
+        assert list(inspect.signature(common.Scene.BA).parameters) == list(sig_before.parameters)
+        for name, p in inspect.signature(common.Scene.BA).parameters.items():
+            assert p.default == sig_before.parameters[name].default
+        # a reference Scene packs to the same x0 through the product's FlatProblem as through the
+        # reference's own BA (duck typing of the two Scene classes)
+        fl, truth, bakw = cases.make('calib_KE')
+        ref = ref_shim.to_reference_scene(fl)
+        fp_ref = FlatProblem(ref, ref.numCam, **bakw)
+        fp_mir = FlatProblem(fl, fl.numCam, **bakw)
+        assert np.abs(fp_ref.x0 - fp_mir.x0).max() <= 1e-12 * max(1.0, np.abs(fp_mir.x0).max())
+        assert fp_ref.N == fp_mir.N and (fp_ref.knots == fp_mir.knots).all()
+    finally:
+        common.Scene.BA = orig
+        common.Scene.error_cam = common.Scene._reference_error_cam
+        common.Scene.remove_outliers = common.Scene._reference_remove_outliers
