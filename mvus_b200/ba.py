@@ -121,6 +121,8 @@ def error_cam(scene, cam_id, mode='dist', motion_prior=False, norm=False):
         dg = hd.detections_global(fp.x0)
     finally:
         hd.close()
+    if len(scene.detections_global) < scene.numCam:       # fresh Scene: detection_to_global not called yet
+        scene.detections_global = list(scene.detections_global) + [[] for _ in range(scene.numCam - len(scene.detections_global))]
     scene.detections_global[cam_id] = dg[0]
     N = fp.N
     eu, ev = r[:N], r[N:2 * N]
