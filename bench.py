@@ -38,8 +38,8 @@ def parse():
     ap.add_argument('--cams', type=int, default=64)
     ap.add_argument('--det', type=int, default=1000000, help='detections per camera')
     ap.add_argument('--coef', type=int, default=200000, help='spline coefficients per axis')
-    ap.add_argument('--sample-cams', type=int, default=4)
-    ap.add_argument('--sample-det', type=int, default=1500)
+    ap.add_argument('--sample-cams', type=int, default=7)
+    ap.add_argument('--sample-det', type=int, default=3000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='cfg4', choices=['cfg4', 'cfg2', 'cfg3', 'cfg5'],
                     help='BASELINE.json config: cfg4 (default, the one the metric is quoted on), cfg2 7x100k RS+F, '
@@ -315,9 +315,18 @@ def main():
               'solve_share_ms': ms[5], 'resjac_share_ms': ms[3], 'accum_share_ms': ms[4], 'trial_share_ms': ms[6]}
     dom = 'resjac_K1' if ms[3] >= ms[4] else 'accumulate_K2'
     ach = phases[dom]['algorithmic_GBps']
+    # DRAM traffic per detection from the round's `ncu --set full` captures at config 4
+    # (profiles/r1_ncu_full_cfg4_{resjac,accumulate}.raw.csv: dram__bytes_read.sum + write.sum over
+    # 64 000 042 detections, P = 21); None for other P
+    ncu_bytes_per_det = {'resjac_K1': 411.0, 'accumulate_K2': 747.8} if P == 21 else {}
+    traffic = ncu_bytes_per_det.get(dom)
     roof = {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-            'traffic': None, 'peak_source': peak_src,
-            'note': 'per-rank detections x %d B/det / CUDA-event time of the kernel run alone (3 reps)' % phases[dom]['bytes_per_det']}
+            'traffic': None if traffic is None else traffic * N_loc / 1e9, 'traffic_unit': 'GB per launch (ncu, config 4 capture scaled by detections)',
+            'peak_source': peak_src,
+            'note': 'per-rank detections x %d B/det / CUDA-event time of the kernel run alone (3 reps)' % phases[dom]['bytes_per_det'],
+            'other_kernel': {'kernel': 'resjac_K1' if dom != 'resjac_K1' else 'accumulate_K2',
+                             'achieved': phases['resjac_K1' if dom != 'resjac_K1' else 'accumulate_K2']['algorithmic_GBps'],
+                             'frac': phases['resjac_K1' if dom != 'resjac_K1' else 'accumulate_K2']['algorithmic_GBps'] / peak}}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps_done, 'warmup': a.warmup,
             'ms_per_step': ms[0] / max(steps_done, 1), 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
