@@ -307,7 +307,8 @@ __global__ void floor_kernel(double* __restrict__ v, int64_t n, const double* __
 // ZR is stored in E[j]; root = final pass on block 0.
 template <int Q>
 __global__ void __launch_bounds__(256, 2)
-bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* __restrict__ Dw,
+bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, int odd_only,
+                 const double* __restrict__ Wsrc, double* __restrict__ Dw,
                  double* __restrict__ Ew, double* __restrict__ Ww, double* __restrict__ ZL,
                  int* __restrict__ fail_flag) {
     constexpr int q = Q;
@@ -319,7 +320,8 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* _
     // apply the pending updates of the last local level and leave the bridged coupling in Ew[j])
     const bool upd_only = (root == 2);
     if (upd_only) root = 0;
-    const int64_t j = root ? 0 : (int64_t)blockIdx.x * s;
+    // odd_only (level 0): only the blocks that are eliminated are launched; survivors have nothing to do
+    const int64_t j = root ? 0 : (odd_only ? (2 * (int64_t)blockIdx.x + 1) * s : (int64_t)blockIdx.x * s);
     const bool elim = !upd_only && (root || (((j / s) & 1) == 1));
     const int tid = threadIdx.x, nt = blockDim.x;
     const int qq = q * q;
@@ -405,10 +407,12 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, double* _
     const double* Wm = Ww + (j - sp) * (int64_t)q * ldw;
     const double* Wp = Ww + (j + sp) * (int64_t)q * ldw;
     double* Wj = Ww + j * (int64_t)q * ldw;
+    // first touch of a block reads the undamped original W~ (no separate working copy pass)
+    const double* Wj_in = Wsrc ? Wsrc + j * (int64_t)q * ldw : Wj;
     for (int c = tid; c < ldw; c += nt) {
         double w[Q];
 #pragma unroll
-        for (int a = 0; a < Q; ++a) w[a] = Wj[(int64_t)a * ldw + c];
+        for (int a = 0; a < Q; ++a) w[a] = Wj_in[(int64_t)a * ldw + c];
         if (has_m)
 #pragma unroll 3
             for (int k = 0; k < Q; ++k) {
@@ -992,11 +996,14 @@ inline int compute_diag(mvus_ba_ctx* h, bool full_everywhere = false) {
 
 struct BcrView {          // a block-tridiagonal system (possibly a sub-range of the handle's arrays)
     double* Dw; double* Ew; double* Ww; double* ZL; double* ds; int64_t nb;
+    const double* Worig = nullptr;   // if set: Ww has NOT been initialised, a block's first touch reads from here
 };
 
-inline void launch_level(mvus_ba_ctx* h, const BcrView& v, int grid, int64_t s, int64_t sp, int root, int* fail_flag) {
+inline void launch_level(mvus_ba_ctx* h, const BcrView& v, int grid, int64_t s, int64_t sp, int root, int* fail_flag,
+                         int odd_only = 0, const double* wsrc = nullptr) {
+    if (grid <= 0) return;
     const int nthr = h->ldw > 192 ? 256 : 128;      // one W~ column per thread and pass
-#define MV_LVL(QQ) bcr_level_kernel<QQ><<<grid, nthr, 0, h->st>>>(v.nb, h->ldw, s, sp, root, v.Dw, v.Ew, v.Ww, v.ZL, fail_flag)
+#define MV_LVL(QQ) bcr_level_kernel<QQ><<<grid, nthr, 0, h->st>>>(v.nb, h->ldw, s, sp, root, odd_only, wsrc, v.Dw, v.Ew, v.Ww, v.ZL, fail_flag)
     switch (h->q) {
         case 9: MV_LVL(9); break;
         case 12: MV_LVL(12); break;
@@ -1013,10 +1020,14 @@ inline std::vector<int64_t> bcr_eliminate(mvus_ba_ctx* h, const BcrView& v, int6
     for (int64_t s = 1; s < s_end && s < v.nb; s <<= 1) levels.push_back(s);
     for (size_t lv = 0; lv < levels.size(); ++lv) {
         const int64_t s = levels[lv], sp = lv ? levels[lv - 1] : 0;
-        launch_level(h, v, (int)((v.nb + s - 1) / s), s, sp, 0, fail_flag);
+        // level 0: only the odd blocks work (no pending updates exist yet); blocks first touched at
+        // level 0 (odd) or 1 (even) read their W~ rows from the original array when no copy was made
+        if (lv == 0) launch_level(h, v, (int)(v.nb / 2), s, sp, 0, fail_flag, 1, v.Worig);
+        else launch_level(h, v, (int)((v.nb + s - 1) / s), s, sp, 0, fail_flag, 0, lv == 1 ? v.Worig : nullptr);
     }
     if (with_root)
-        launch_level(h, v, 1, levels.empty() ? 1 : levels.back() * 2, levels.empty() ? 0 : levels.back(), 1, fail_flag);
+        launch_level(h, v, 1, levels.empty() ? 1 : levels.back() * 2, levels.empty() ? 0 : levels.back(), 1, fail_flag,
+                     0, levels.size() <= 1 ? v.Worig : nullptr);
     return levels;
 }
 
@@ -1091,13 +1102,15 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
         damp_copy_kernel<<<(int)((nbq * q + 255) / 256), 256, 0, h->st>>>(h->D.p, h->diag_s.p, lam, nbq, q,
                                                                           3 * h->n_ctrl, h->Dw.p);
         MV_CUDA(h, cudaMemcpyAsync(h->Ew.p, h->E.p, nb * qq * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-        MV_CUDA(h, cudaMemcpyAsync(h->Ww.p, h->W.p, (size_t)nbq * ldw * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
         h->launches += 1;
-        if (h->desc.rs_bounds) {
+        BcrView v{h->Dw.p, h->Ew.p, h->Ww.p, h->ZL.p, h->dlt_s.p, nb};
+        if (h->desc.rs_bounds) {          // frozen columns must be zeroed in a private copy
+            MV_CUDA(h, cudaMemcpyAsync(h->Ww.p, h->W.p, (size_t)nbq * ldw * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
             freeze_cols_kernel<<<(int)((nbq + 255) / 256), 256, 0, h->st>>>(h->Ww.p, nbq, ldw, h->nc, h->Pc, h->frozen.p);
             h->launches++;
+        } else {
+            v.Worig = h->W.p;             // first touch of every block reads W~ directly: no 2|W~| copy pass
         }
-        BcrView v{h->Dw.p, h->Ew.p, h->Ww.p, h->ZL.p, h->dlt_s.p, nb};
         std::vector<int64_t> levels = bcr_eliminate(h, v, nb, true, fail_flag);
         launch_syrk(h, h->Ww.p, nbq, h->Sd.p);
         form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
