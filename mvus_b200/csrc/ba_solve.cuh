@@ -306,7 +306,7 @@ __global__ void floor_kernel(double* __restrict__ v, int64_t n, const double* __
 //   - if j is an odd multiple of s (or the root pass): factor D_j, form ZL/ZR/W~ rows.
 // ZR is stored in E[j]; root = final pass on block 0.
 template <int Q>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 4)
 bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, int odd_only,
                  const double* __restrict__ Wsrc, double* __restrict__ Dw,
                  double* __restrict__ Ew, double* __restrict__ Ww, double* __restrict__ ZL,
