@@ -79,7 +79,7 @@ struct mvus_ba_ctx {
     mvus::DevBuf<unsigned char> tau_flag;
 
     // per-evaluation state
-    mvus::DevBuf<double> x, x_trial, camprep, r, J, mJ, partial, scratch;
+    mvus::DevBuf<double> x, x_trial, camprep, r, J, mJ, partial, scratch, gt_out;
     mvus::DevBuf<int> span, mbase, flag, frozen;
     double* h_pin = nullptr;      // pinned scratch for scalars
     size_t h_pin_n = 0;

@@ -79,7 +79,7 @@ extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
                     &h->int_b, &h->knots, &h->spanpoly, &h->span_t0, &h->lut_t0, &h->lut_invh, &h->tau,
                     &h->x, &h->x_trial, &h->camprep, &h->r, &h->J, &h->mJ, &h->partial, &h->A, &h->D, &h->E,
                     &h->W, &h->Dw, &h->Ew, &h->Ww, &h->ZL, &h->Sd, &h->dlt_c, &h->dlt_s, &h->diag_c,
-                    &h->diag_s, &h->gvec, &h->xs, &h->scratch, &h->Dt, &h->ZLt, &h->dst, &h->bs})
+                    &h->diag_s, &h->gvec, &h->xs, &h->scratch, &h->gt_out, &h->Dt, &h->ZLt, &h->dst, &h->bs})
         b->release();
     for (auto* b : {&h->row_off, &h->tile_start, &h->knot_off, &h->ctrl_off, &h->xoff, &h->lut_off}) b->release();
     for (auto* b : {&h->tile_cam, &h->tile_cnt, &h->ncoef, &h->deg, &h->lut_n, &h->lut, &h->tau_spl, &h->span,
@@ -726,13 +726,13 @@ extern "C" int mvus_ba_global_traj(mvus_ba_handle h, const double* x, const int3
     const int64_t n = (int64_t)last_pos + last_flag;
     *n_out = n;
     if (n > 0) {
-        e = h->scratch.alloc((size_t)7 * n);
+        e = h->gt_out.alloc((size_t)7 * N);                // sized for the worst case: allocated once
         if (e == cudaSuccess) {
             gt_gather_kernel<<<gb, 256, 0, h->st>>>(h->sv, h->x.p, ts_s.p, idx_s.p, flag.p, pos.p, N, n, h->row_off.p,
-                                                   h->nc, cams.p, h->frame.p, h->scratch.p);
+                                                   h->nc, cams.p, h->frame.p, h->gt_out.p);
             e = cudaGetLastError();
         }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out, h->scratch.p, (size_t)7 * n * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, h->gt_out.p, (size_t)7 * n * sizeof(double), cudaMemcpyDeviceToHost, h->st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
     }
     cleanup();
@@ -760,7 +760,7 @@ extern "C" int mvus_ba_visibility(mvus_ba_handle h, const double* x, int64_t* vi
     MV_CUDA(h, cudaMemcpyAsync(h->x.p, x, h->n * sizeof(double), cudaMemcpyHostToDevice, h->st));
     cam_prep_kernel<<<(h->nc + 63) / 64, 64, 0, h->st>>>(h->x.p, h->nc, h->C, h->desc.opt_calib, h->calib.p,
                                                          h->height.p, h->camprep.p);
-    MV_CUDA(h, h->scratch.alloc((size_t)h->N));
+    MV_CUDA(h, h->scratch.alloc((size_t)3 * h->N));      // sized for detections_global: allocated once
     visibility_kernel<<<h->n_tiles, TILE_DET, 0, h->st>>>(h->sv, h->camprep.p, h->tile_cam.p, h->tile_start.p,
                                                          h->tile_cnt.p, h->frame.p, h->yr.p,
                                                          reinterpret_cast<long long*>(h->scratch.p));
