@@ -162,9 +162,11 @@ void  mvus_ba_host_free(void* p);
  * `global_traj` = every detection of the optimised cameras whose global time stamp lies inside
  * a spline interval (closed ends, common.py:292), sorted by time stamp.  out: 7 x n_out
  * row-major (rows: running index, camera id taken from cam_ids[nc], frame id, time stamp,
- * X, Y, Z of the spline at that time); the buffer must hold 7*N doubles. */
+ * X, Y, Z of the spline at that time); the buffer must hold 7*N doubles.
+ * gd_out (may be NULL): `global_detections` (common.py:927), 3 x N row-major = camera id, frame
+ * id, global time stamp of every detection in concatenation order. */
 int mvus_ba_global_traj(mvus_ba_handle h, const double* x, const int32_t* cam_ids, int64_t* n_out,
-                        double* out);
+                        double* out, double* gd_out);
 
 /* Diagnostics used by the parity tests: the normal equations K2 assembles at x.
  *   A    [nc*Pc*Pc]  camera diagonal blocks (Pc = 3 + C), row-major per camera

@@ -74,7 +74,7 @@ def load():
     lib.mvus_ba_solve.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, ctypes.POINTER(BAStats)]
     lib.mvus_ba_detections_global.argtypes = [ctypes.c_void_p, _dp, _dp]
     lib.mvus_ba_normal_equations.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp, _ip, _dp, _dp]
-    lib.mvus_ba_global_traj.argtypes = [ctypes.c_void_p, _dp, _ip, _lp, _dp]
+    lib.mvus_ba_global_traj.argtypes = [ctypes.c_void_p, _dp, _ip, _lp, _dp, _dp]
     lib.mvus_ba_visibility.argtypes = [ctypes.c_void_p, _dp, _lp]
     lib.mvus_ba_host_alloc.argtypes = [ctypes.c_size_t]
     lib.mvus_ba_host_alloc.restype = ctypes.c_void_p
@@ -238,9 +238,10 @@ class Handle:
         x = np.ascontiguousarray(x, dtype=np.float64)
         ids = np.ascontiguousarray(cam_ids, dtype=np.int32)
         out = POOL.empty(7 * max(self.N, 1))
+        gd = POOL.empty(3 * max(self.N, 1))
         n = ctypes.c_int64()
-        self._check(self.lib.mvus_ba_global_traj(self.h, _d(x), _i(ids), ctypes.byref(n), _d(out)))
-        return out[:7 * n.value].reshape(7, n.value)
+        self._check(self.lib.mvus_ba_global_traj(self.h, _d(x), _i(ids), ctypes.byref(n), _d(out), _d(gd)))
+        return out[:7 * n.value].reshape(7, n.value), gd[:3 * self.N].reshape(3, self.N)
 
     def normal_equations(self, x, want_dense=True):
         fp = self.fp

@@ -186,19 +186,12 @@ def _all_detect_to_traj(scene, fp, hd, x):
     frame_id_all, global_detections from the refreshed detections_global; global_traj (sorted,
     in-interval detections with their spline positions) from the device (mvus_ba_global_traj)."""
     cams = fp.seq
-    N = fp.N
     # drop the previous call's arrays first so that their pinned blocks are reused
     scene.global_detections = scene.frame_id_all = scene.global_time_stamps_all = scene.global_traj = None
-    gd = _cabi.POOL.empty(3 * N).reshape(3, N)
-    for k, i in enumerate(cams):
-        a, b = fp.cam_ptr[k], fp.cam_ptr[k + 1]
-        gd[0, a:b] = i
-        gd[1, a:b] = fp.dets[k][0]
-        gd[2, a:b] = scene.detections_global[i][0]
+    scene.global_traj, gd = hd.global_traj(x, cams)
     scene.global_detections = gd
     scene.frame_id_all = gd[1]                 # views of global_detections (same values, no copy)
     scene.global_time_stamps_all = gd[2]
-    scene.global_traj = hd.global_traj(x, cams)
 
 
 def bundle_adjust(scene, numCam, max_iter=10, rs=False, motion_prior=False, motion_reg=False,

@@ -23,6 +23,22 @@ __global__ void gt_times_kernel(const double* __restrict__ camprep, const int* _
     idx[d] = (int)d;
 }
 
+// global_detections (common.py:927): rows camera id, frame id, global time stamp, in the
+// concatenation order of the optimised cameras.  out[3][N]
+__global__ void gd_kernel(const double* __restrict__ camprep, const int* __restrict__ tile_cam,
+                          const int64_t* __restrict__ tile_start, const int* __restrict__ tile_cnt,
+                          const double* __restrict__ frame, const double* __restrict__ yr,
+                          const int* __restrict__ cam_ids, int64_t N, double* __restrict__ out) {
+    const int tl = blockIdx.x;
+    if ((int)threadIdx.x >= tile_cnt[tl]) return;
+    const int cam = tile_cam[tl];
+    const CamPrep& c = *reinterpret_cast<const CamPrep*>(camprep + (size_t)cam * CAMPREP_DOUBLES);
+    const int64_t d = tile_start[tl] + threadIdx.x;
+    out[d] = (double)cam_ids[cam];
+    out[N + d] = frame[d];
+    out[2 * N + d] = c.alpha * (frame[d] + c.rho * (yr[d] * c.invH)) + c.beta;
+}
+
 __device__ __forceinline__ int closed_interval(const SplineView& sp, double t) {
     for (int s = 0; s < sp.S; ++s)
         if (t >= sp.int_a[s] && t <= sp.int_b[s]) return s;

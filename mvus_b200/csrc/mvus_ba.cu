@@ -683,7 +683,7 @@ extern "C" int mvus_ba_time_accumulate(mvus_ba_handle h, int32_t reps, double* m
 
 // ------------------------------------------------------------------------------------------
 extern "C" int mvus_ba_global_traj(mvus_ba_handle h, const double* x, const int32_t* cam_ids,
-                                   int64_t* n_out, double* out) {
+                                   int64_t* n_out, double* out, double* gd_out) {
     int rc = check_ready(h);
     if (rc) return rc;
     if (!x || !cam_ids || !n_out || !out) return fail(h, MVUS_ERR_ARG, "null argument");
@@ -710,6 +710,15 @@ extern "C" int mvus_ba_global_traj(mvus_ba_handle h, const double* x, const int3
     if (e == cudaSuccess) e = tmp.alloc(tb);
     auto cleanup = [&]() { ts.release(); ts_s.release(); idx.release(); idx_s.release(); flag.release(); pos.release(); cams.release(); tmp.release(); };
     if (e != cudaSuccess) { cleanup(); return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e)); }
+    if (gd_out) {          // global_detections: 3 x N (camera id, frame id, time stamp), concatenation order
+        e = h->scratch.alloc((size_t)3 * N);
+        if (e == cudaSuccess) {
+            gd_kernel<<<h->n_tiles, TILE_DET, 0, h->st>>>(h->camprep.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p,
+                                                         h->frame.p, h->yr.p, cams.p, N, h->scratch.p);
+            e = cudaMemcpyAsync(gd_out, h->scratch.p, (size_t)3 * N * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+        }
+        if (e != cudaSuccess) { cleanup(); return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e)); }
+    }
     gt_times_kernel<<<h->n_tiles, TILE_DET, 0, h->st>>>(h->camprep.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p,
                                                        h->frame.p, h->yr.p, ts.p, idx.p);
     e = cub::DeviceRadixSort::SortPairs(tmp.p, tb, ts.p, ts_s.p, idx.p, idx_s.p, (int)N, 0, 64, h->st);

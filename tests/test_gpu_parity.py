@@ -176,6 +176,11 @@ def test_scene_ba_postconditions(built_lib):
     assert (gt[:3] == fl.global_traj[:3]).all()                     # index, camera, frame (same order)
     assert np.abs(gt[3:] - fl.global_traj[3:]).max() <= 1e-9 * max(1.0, np.abs(gt[3:]).max())
     assert fl.global_detections.shape == (3, sum(d.shape[1] for d in fl.detections))
+    cams = list(range(fl.numCam))
+    assert np.array_equal(fl.global_detections[0], np.concatenate([np.full(fl.detections[i].shape[1], float(i)) for i in cams]))
+    assert np.array_equal(fl.global_detections[1], np.concatenate([fl.detections[i][0] for i in cams]))
+    assert np.array_equal(fl.global_detections[2], np.concatenate([fl.detections_global[i][0] for i in cams]))
+    assert np.array_equal(fl.frame_id_all, fl.global_detections[1])
     import pickle
     pickle.dumps(fl)
 
