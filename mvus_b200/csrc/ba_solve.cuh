@@ -141,9 +141,25 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
         typ[k] = K2_NONE; sa[k] = 0; sb[k] = 0; xa[k] = 0; xb[k] = 0; cacc[k] = 0.0;
         pa[k] = s_J; pb[k] = s_J;
         if (e < Cfg::NE) {
-            int a = 0;
-            while (e >= (P + 1 - a)) { e -= (P + 1 - a); ++a; }
-            const int b = a + e;
+            // Entry enumeration chosen for coalescing: camera x control entries are ordered
+            // control-row-major, so 9 (18) consecutive lanes RED into contiguous columns of ONE W~ row
+            // (72 B = 3 sectors instead of 9 rows) and share their control operand in shared memory;
+            // control x control entries are row-major in the 12 x 12 block.
+            const int nCC = Pc * 12;                       // camera x control
+            int a, b;
+            if (e < nCC) { b = Pc + e / Pc; a = e - (e / Pc) * Pc; }
+            else if (e < nCC + 12) { a = Pc + (e - nCC); b = P; }                         // control x residual
+            else if (e < nCC + 12 + 78) {                                                 // control x control, la <= lb
+                int t = e - nCC - 12, ra = 0;
+                while (t >= 12 - ra) { t -= 12 - ra; ++ra; }
+                a = Pc + ra; b = Pc + ra + t;
+            } else {                                                                       // camera x camera / residual
+                int t = e - nCC - 12 - 78, ra = 0;
+                while (t >= Pc + 1 - ra) { t -= Pc + 1 - ra; ++ra; }
+                a = ra; b = ra + t;
+                if (b == Pc) b = P;                        // last column of that triangle = residual
+                if (a == Pc) { a = P; b = P; }             // residual x residual (cost; not accumulated)
+            }
             pa[k] = s_J + a * LDT; pb[k] = s_J + b * LDT;
             if (a < Pc) {
                 if (b < Pc) { typ[k] = K2_CAMCAM; xa[k] = a; xb[k] = b; }

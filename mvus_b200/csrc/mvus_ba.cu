@@ -454,6 +454,8 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
     // lambda costs linear solves but no residual evaluations (nfev is what max_iter caps).
     const double lam_min = 1e-10;
     const bool verbose = getenv("MVUS_BA_VERBOSE") != nullptr;
+    const double band_lo = getenv("MVUS_BA_BAND_LO") ? atof(getenv("MVUS_BA_BAND_LO")) : 0.5;
+    const double band_hi = getenv("MVUS_BA_BAND_HI") ? atof(getenv("MVUS_BA_BAND_HI")) : 1.5;
     double lam = 1e-4, Delta = -1.0;
     double pexp = 2.0 / 3.0;          // running estimate of p in |delta|_D ~ lambda^-p
     double last_l = -1.0, last_n = 0.0;
@@ -496,8 +498,8 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
         // bracket / secant search on lambda (log scale) for |delta|_D ~ Delta
         double lo_l = -1, lo_n = 0, hi_l = -1, hi_n = 0;
         for (int its = 0; its < 10; ++its) {
-            if (!ok || nrm > 1.5 * Delta) { lo_l = lam; lo_n = nrm; }
-            else if (nrm < 0.5 * Delta && lam > lam_min) { hi_l = lam; hi_n = nrm; }
+            if (!ok || nrm > band_hi * Delta) { lo_l = lam; lo_n = nrm; }
+            else if (nrm < band_lo * Delta && lam > lam_min) { hi_l = lam; hi_n = nrm; }
             else break;
             if (lo_l > 0 && hi_l > 0 && lo_n < 1e299) {
                 // bracketed: |delta|_D(lambda) is monotone but has plateaus and cliffs, so interpolate
