@@ -168,6 +168,13 @@ void  mvus_ba_host_free(void* p);
 int mvus_ba_global_traj(mvus_ba_handle h, const double* x, const int32_t* cam_ids, int64_t* n_out,
                         double* out, double* gd_out);
 
+/* Scene.spline_to_traj (common.py:273-301): evaluate the splines (coefficients inside x) at the
+ * ascending times t[n]; a time is kept iff it lies inside a spline interval (closed ends,
+ * common.py:292).  out: 4 x n_out row-major (time, X, Y, Z); the buffer must hold 4*n doubles.
+ * Needs mvus_ba_set_splines only (no detections). */
+int mvus_ba_spline_to_traj(mvus_ba_handle h, const double* x, const double* t, int64_t n,
+                           int64_t* n_out, double* out);
+
 /* Diagnostics used by the parity tests: the normal equations K2 assembles at x.
  *   A    [nc*Pc*Pc]  camera diagonal blocks (Pc = 3 + C), row-major per camera
  *   g    [n]         J^T r in the reference's x layout

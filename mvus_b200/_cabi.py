@@ -38,7 +38,7 @@ class BAStats(ctypes.Structure):
 EXPORTS = ['mvus_ba_version', 'mvus_ba_create', 'mvus_ba_destroy', 'mvus_ba_last_error',
            'mvus_ba_set_detections', 'mvus_ba_set_detections_rows', 'mvus_ba_set_splines', 'mvus_ba_dims', 'mvus_ba_residual',
            'mvus_ba_residual_jacobian', 'mvus_ba_solve', 'mvus_ba_detections_global',
-           'mvus_ba_normal_equations', 'mvus_ba_global_traj', 'mvus_ba_visibility', 'mvus_ba_host_alloc',
+           'mvus_ba_normal_equations', 'mvus_ba_global_traj', 'mvus_ba_spline_to_traj', 'mvus_ba_visibility', 'mvus_ba_host_alloc',
            'mvus_ba_host_free', 'mvus_ba_nccl_unique_id', 'mvus_ba_comm_init',
            'mvus_ba_time_resjac', 'mvus_ba_time_accumulate']
 
@@ -75,6 +75,7 @@ def load():
     lib.mvus_ba_detections_global.argtypes = [ctypes.c_void_p, _dp, _dp]
     lib.mvus_ba_normal_equations.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp, _ip, _dp, _dp]
     lib.mvus_ba_global_traj.argtypes = [ctypes.c_void_p, _dp, _ip, _lp, _dp, _dp]
+    lib.mvus_ba_spline_to_traj.argtypes = [ctypes.c_void_p, _dp, _dp, ctypes.c_int64, _lp, _dp]
     lib.mvus_ba_visibility.argtypes = [ctypes.c_void_p, _dp, _lp]
     lib.mvus_ba_host_alloc.argtypes = [ctypes.c_size_t]
     lib.mvus_ba_host_alloc.restype = ctypes.c_void_p
@@ -233,6 +234,15 @@ class Handle:
         self._check(self.lib.mvus_ba_visibility(self.h, _d(x), _l(out)))
         cp = self.fp.cam_ptr
         return [out[cp[k]:cp[k + 1]] for k in range(self.fp.nc)]
+
+    def spline_to_traj(self, x, t):
+        """4 x n' array [t; X; Y; Z] of the splines in x at the ascending times t inside the intervals."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        out = np.empty(4 * max(len(t), 1))
+        n = ctypes.c_int64()
+        self._check(self.lib.mvus_ba_spline_to_traj(self.h, _d(x), _d(t), len(t), ctypes.byref(n), _d(out)))
+        return out[:4 * n.value].reshape(4, n.value)
 
     def global_traj(self, x, cam_ids):
         x = np.ascontiguousarray(x, dtype=np.float64)

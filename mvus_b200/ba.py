@@ -154,30 +154,42 @@ def remove_outliers(scene, cams, thres=30, verbose=False):
                 int(np.sum(err >= thres)), int(np.sum(err != 0)), i))
 
 
-def _bspline_eval(t, tck):
-    """splev(t, tck) for the bookkeeping outputs (traj); scipy when present."""
-    from scipy import interpolate
-    return np.asarray(interpolate.splev(t, tck))
+def _spline_only_problem(scene):
+    """A FlatProblem with the Scene's splines and one camera without detections: enough for the
+    entry points that only evaluate splines."""
+    class _S:
+        pass
+    s = _S()
+    s.__dict__.update({k: getattr(scene, k) for k in ('settings', 'alpha', 'beta', 'rs', 'spline')})
+    s.cameras = scene.cameras
+    s.detections = list(scene.detections)
+    i0 = 0
+    s.detections[i0] = np.zeros((3, 0))
+    s.sequence = [i0]
+    return FlatProblem(s, 1)
 
 
-def spline_to_traj(scene, sampling_rate=1, t=None):
-    """Scene.spline_to_traj (common.py:273-301): host-side bookkeeping output (pickled
-    ``traj``); not part of the residual evaluation, which samples on the device."""
-    tck, interval = scene.spline['tck'], np.asarray(scene.spline['int'])
-    scene.traj = np.empty([4, 0])
+def spline_to_traj(scene, sampling_rate=1, t=None, hd=None, x=None):
+    """Scene.spline_to_traj (common.py:273-301) through the library (mvus_ba_spline_to_traj):
+    samples the splines at a constant rate or at the given ascending time stamps and stores the
+    4 x n result in ``scene.traj``."""
+    interval = np.asarray(scene.spline['int'])
     if t is not None:
         assert len(t.shape) == 1, 'Input timestamps must be a 1D array'
-        timestamp = t
+        timestamp = np.asarray(t, dtype=np.float64)
     else:
         timestamp = np.arange(interval[0, 0], interval[1, -1], sampling_rate)
-    for i in range(interval.shape[1]):
-        t_part = timestamp[np.logical_and(timestamp >= interval[0, i], timestamp <= interval[1, i])]
-        try:
-            part = _bspline_eval(t_part, tck[i])
-        except Exception:
-            continue
-        scene.traj = np.hstack((scene.traj, np.vstack((t_part, part))))
-    assert (scene.traj[0, 1:] >= scene.traj[0, :-1]).all()
+    assert (timestamp[1:] >= timestamp[:-1]).all(), 'time stamps must be ascending'
+    own = hd is None
+    if own:
+        fp = _spline_only_problem(scene)
+        hd = _cabi.Handle(fp, device=DEVICE)
+        x = fp.x0
+    try:
+        scene.traj = hd.spline_to_traj(x, timestamp)
+    finally:
+        if own:
+            hd.close()
     return scene.traj
 
 
@@ -264,7 +276,7 @@ def bundle_adjust(scene, numCam, max_iter=10, rs=False, motion_prior=False, moti
         lap('refresh_ms')
         if motion_reg and bookkeeping:
             _all_detect_to_traj(scene, fp, hd, x)
-            spline_to_traj(scene)           # common.py:379 leaves traj = unit-step samples
+            spline_to_traj(scene, hd=hd, x=x)   # common.py:379 leaves traj = unit-step samples
             lap('bookkeeping_ms')
     finally:
         if not return_handle:

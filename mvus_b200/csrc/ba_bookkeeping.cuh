@@ -75,4 +75,25 @@ __global__ void gt_gather_kernel(SplineView sp, const double* __restrict__ x, co
     out[6 * n_out + o] = X[2];
 }
 
+// Scene.spline_to_traj (common.py:273-301): evaluate the splines at ascending times t; a time is
+// kept iff it lies inside a spline interval (closed ends, common.py:292).
+__global__ void s2t_flag_kernel(SplineView sp, const double* __restrict__ t, int64_t n, int* __restrict__ flag) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) flag[k] = closed_interval(sp, t[k]) >= 0 ? 1 : 0;
+}
+__global__ void s2t_gather_kernel(SplineView sp, const double* __restrict__ x, const double* __restrict__ t,
+                                  const int* __restrict__ flag, const int* __restrict__ pos, int64_t n,
+                                  int64_t n_out, double* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n || !flag[k]) return;
+    const int64_t o = pos[k];
+    const double tt = t[k];
+    double X[3], dX[3], B[4];
+    spline_eval<false>(sp, x, closed_interval(sp, tt), tt, X, dX, B);
+    out[o] = tt;
+    out[n_out + o] = X[0];
+    out[2 * n_out + o] = X[1];
+    out[3 * n_out + o] = X[2];
+}
+
 }  // namespace mvus

@@ -780,3 +780,50 @@ extern "C" int mvus_ba_visibility(mvus_ba_handle h, const double* x, int64_t* vi
     MV_CUDA(h, cudaStreamSynchronize(h->st));
     return MVUS_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+extern "C" int mvus_ba_spline_to_traj(mvus_ba_handle h, const double* x, const double* t, int64_t n,
+                                      int64_t* n_out, double* out) {
+    if (!h) return MVUS_ERR_ARG;
+    if (!h->have_spl) return fail(h, MVUS_ERR_ARG, "set_splines first");
+    if (!x || !n_out || !out || (n > 0 && !t)) return fail(h, MVUS_ERR_ARG, "null argument");
+    MV_CUDA(h, cudaSetDevice(h->desc.device));
+    *n_out = 0;
+    if (n == 0) return MVUS_OK;
+    if (n >= (int64_t)1 << 31) return fail(h, MVUS_ERR_UNSUPPORTED, "more than 2^31 sample times");
+    const int64_t nx = h->n_other + 3 * h->n_ctrl;
+    DevBuf<double> xd, td, od;
+    DevBuf<int> flag, pos;
+    DevBuf<unsigned char> tmp;
+    auto cleanup = [&]() { xd.release(); td.release(); od.release(); flag.release(); pos.release(); tmp.release(); };
+    cudaError_t e = upload(xd, x, (size_t)nx, h->st);
+    if (e == cudaSuccess) e = upload(td, t, (size_t)n, h->st);
+    if (e == cudaSuccess) e = flag.alloc(n);
+    if (e == cudaSuccess) e = pos.alloc(n);
+    size_t tb = 0;
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tb, flag.p, pos.p, (int)n, h->st);
+    if (e == cudaSuccess) e = tmp.alloc(tb);
+    const int gb = (int)((n + 255) / 256);
+    if (e == cudaSuccess) {
+        s2t_flag_kernel<<<gb, 256, 0, h->st>>>(h->sv, td.p, n, flag.p);
+        e = cub::DeviceScan::ExclusiveSum(tmp.p, tb, flag.p, pos.p, (int)n, h->st);
+    }
+    int lp = 0, lf = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&lp, pos.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&lf, flag.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    if (e != cudaSuccess) { cleanup(); return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e)); }
+    const int64_t m = (int64_t)lp + lf;
+    *n_out = m;
+    if (m > 0) {
+        e = od.alloc((size_t)4 * m);
+        if (e == cudaSuccess) {
+            s2t_gather_kernel<<<gb, 256, 0, h->st>>>(h->sv, xd.p, td.p, flag.p, pos.p, n, m, od.p);
+            e = cudaMemcpyAsync(out, od.p, (size_t)4 * m * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    }
+    cleanup();
+    if (e != cudaSuccess) return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e));
+    return MVUS_OK;
+}

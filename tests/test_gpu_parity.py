@@ -385,3 +385,34 @@ def test_rs_bounds_keep_rho_in_box(built_lib):
     res = fl.BA(fl.numCam, max_iter=15, **bakw)
     assert (fl.rs >= 0.0).all() and (fl.rs <= 1.0).all()
     assert res.cost < res.stats['cost0']
+
+
+def test_spline_to_traj_matches_scipy(built_lib):
+    """Scene.spline_to_traj (common.py:273-301) through mvus_ba_spline_to_traj vs scipy.splev:
+    unit-rate sampling and explicit time stamps (inside, in the gap, outside, on the closed ends)."""
+    from scipy.interpolate import splev
+    fl, truth, bakw = cases.make('rs_F_gap')
+    interval = np.asarray(fl.spline['int'])
+    assert interval.shape[1] >= 2
+
+    def expect(ts):
+        parts = []
+        for i in range(interval.shape[1]):
+            tp = ts[(ts >= interval[0, i]) & (ts <= interval[1, i])]
+            parts.append(np.vstack((tp, np.asarray(splev(tp, fl.spline['tck'][i])))))
+        return np.hstack(parts)
+
+    ts = np.arange(interval[0, 0], interval[1, -1], 1.0)
+    got = fl.spline_to_traj()
+    want = expect(ts)
+    assert got.shape == want.shape and got is fl.traj
+    assert (got[0] == want[0]).all()
+    assert np.abs(got[1:] - want[1:]).max() <= 1e-10 * max(1.0, np.abs(want[1:]).max())
+    ts = np.sort(np.concatenate((np.linspace(interval[0, 0] - 20, interval[1, -1] + 20, 777),
+                                 interval.ravel())))
+    got = fl.spline_to_traj(t=ts)
+    want = expect(ts)
+    assert got.shape == want.shape and got.shape[1] < len(ts)
+    assert (got[0] == want[0]).all()
+    assert np.abs(got[1:] - want[1:]).max() <= 1e-10 * max(1.0, np.abs(want[1:]).max())
+    assert fl.spline_to_traj(t=np.array([interval[1, -1] + 5.0])).shape == (4, 0)
