@@ -16,6 +16,7 @@
 // 1e12, far outside what CG in FP64 resolves; LM needs accurate steps along those modes.
 #pragma once
 #include "ba_ctx.cuh"
+#include "ba_k2.cuh"
 
 namespace mvus {
 
@@ -33,7 +34,7 @@ constexpr double DIAG_MIN = 1e-6, DIAG_MAX = 1e32, DIAG_FLOOR_FRAC = 1e-2;
 // HBM traffic per detection (algorithmic): read r (16 B) + span (4 B) + J (16 P B)
 //   -> 356 B (P=21) / 500 B (P=30); writes are O(runs), not O(detections).
 template <int P>
-struct K2Cfg {
+struct K2ScalarCfg {
     static constexpr int NE = (P + 1) * (P + 2) / 2;
     static constexpr int THREADS = 256;
     static constexpr int EPT = (NE + THREADS - 1) / THREADS;
@@ -52,12 +53,12 @@ enum { K2_NONE = 0, K2_CAMCAM, K2_CAMRES, K2_CAMCTRL, K2_CTRLCTRL, K2_CTRLRES };
 // the control point, so a flush is 1-2 shared loads, one 64-bit multiply-add and the RED.
 template <int P>
 __global__ void __launch_bounds__(256)
-accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, const int* __restrict__ span,
+accumulate_scalar_kernel(const double* __restrict__ J, const double* __restrict__ r, const int* __restrict__ span,
                   const int* __restrict__ tile_cam, const int64_t* __restrict__ tile_start,
                   const int* __restrict__ tile_cnt, const int64_t* __restrict__ row_off, int64_t N,
                   int Pc, int bw, int ldw, double* __restrict__ A, double* __restrict__ bc,
                   double* __restrict__ D, double* __restrict__ E, double* __restrict__ W) {
-    using Cfg = K2Cfg<P>;
+    using Cfg = K2ScalarCfg<P>;
     constexpr int LDT = Cfg::LDT;
     extern __shared__ double s_mem[];
     double* s_J = s_mem;                                        // [2*(P+1)][LDT]
@@ -957,16 +958,29 @@ inline int accumulate(mvus_ba_ctx* h) {
     MV_CUDA(h, cudaMemsetAsync(h->E.p, 0, h->nb * qq * sizeof(double), h->st));
     MV_CUDA(h, cudaMemsetAsync(h->W.p, 0, (size_t)h->nb * h->q * h->ldw * sizeof(double), h->st));
     if (h->n_tiles > 0) {
-        if (h->P == 21) {
+        static const bool scalar_k2 = [] { const char* e = getenv("MVUS_BA_K2"); return e && !strcmp(e, "scalar"); }();
+        if (scalar_k2) {
+            if (h->P == 21) {
+                MV_CUDA(h, cudaFuncSetAttribute(accumulate_scalar_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2ScalarCfg<21>::SMEM));
+                accumulate_scalar_kernel<21><<<h->n_tiles, 256, K2ScalarCfg<21>::SMEM, h->st>>>(
+                    h->J.p, h->r.p, h->span.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
+                    h->Pc, h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
+            } else {
+                MV_CUDA(h, cudaFuncSetAttribute(accumulate_scalar_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2ScalarCfg<30>::SMEM));
+                accumulate_scalar_kernel<30><<<h->n_tiles, 256, K2ScalarCfg<30>::SMEM, h->st>>>(
+                    h->J.p, h->r.p, h->span.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
+                    h->Pc, h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
+            }
+        } else if (h->P == 21) {
             MV_CUDA(h, cudaFuncSetAttribute(accumulate_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2Cfg<21>::SMEM));
-            accumulate_kernel<21><<<h->n_tiles, 256, K2Cfg<21>::SMEM, h->st>>>(
+            accumulate_kernel<21><<<h->n_tiles, K2Cfg<21>::THREADS, K2Cfg<21>::SMEM, h->st>>>(
                 h->J.p, h->r.p, h->span.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
-                h->Pc, h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
+                h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
         } else {
             MV_CUDA(h, cudaFuncSetAttribute(accumulate_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2Cfg<30>::SMEM));
-            accumulate_kernel<30><<<h->n_tiles, 256, K2Cfg<30>::SMEM, h->st>>>(
+            accumulate_kernel<30><<<h->n_tiles, K2Cfg<30>::THREADS, K2Cfg<30>::SMEM, h->st>>>(
                 h->J.p, h->r.p, h->span.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
-                h->Pc, h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
+                h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
         }
         h->launches++;
     }
