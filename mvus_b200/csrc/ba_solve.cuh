@@ -25,209 +25,6 @@ int evaluate(mvus_ba_ctx* h, const double* xd, bool want_j);
 constexpr int QMAX = 18;          // 3 * max control points per super-block (bw <= 6)
 constexpr double DIAG_MIN = 1e-6, DIAG_MAX = 1e32, DIAG_FLOOR_FRAC = 1e-2;
 
-// ------------------------------------------------------------------------------------------
-// K2: one CTA per tile of TILE_DET detections of one camera.  The tile's block rows
-// (2 x (P+1) values per detection: Jacobian planes + residual) are staged in shared memory;
-// thread e owns entry (a, b), a <= b, of the per-detection symmetric (P+1) x (P+1) outer
-// product and walks the tile, flushing control-point entries with one FP64 atomic per run of
-// equal span index and camera-only entries once per tile.
-// HBM traffic per detection (algorithmic): read r (16 B) + span (4 B) + J (16 P B)
-//   -> 356 B (P=21) / 500 B (P=30); writes are O(runs), not O(detections).
-template <int P>
-struct K2ScalarCfg {
-    static constexpr int NE = (P + 1) * (P + 2) / 2;
-    static constexpr int THREADS = 256;
-    static constexpr int EPT = (NE + THREADS - 1) / THREADS;
-    static constexpr int LDT = TILE_DET + 1;
-    // J planes + span + run table (start, g, 4 x (block, row))
-    static constexpr size_t SMEM = (size_t)(2 * (P + 1)) * LDT * sizeof(double) +
-                                   (size_t)(TILE_DET + (TILE_DET + 1) + TILE_DET + 8 * TILE_DET + 8) * sizeof(int);
-};
-
-enum { K2_NONE = 0, K2_CAMCAM, K2_CAMRES, K2_CAMCTRL, K2_CTRLCTRL, K2_CTRLRES };
-
-// v2b: same mapping as v2 (thread e owns entry (a, b) of the per-detection outer product, all
-// warps work on the same run) with the per-run flush reduced to a few instructions: everything
-// that depends only on the thread's entry (type, slots, axes, camera column) is computed once, and
-// the run table carries, per run and slot, the super-block and the global row (kb*q + 3*local) of
-// the control point, so a flush is 1-2 shared loads, one 64-bit multiply-add and the RED.
-template <int P>
-__global__ void __launch_bounds__(256)
-accumulate_scalar_kernel(const double* __restrict__ J, const double* __restrict__ r, const int* __restrict__ span,
-                  const int* __restrict__ tile_cam, const int64_t* __restrict__ tile_start,
-                  const int* __restrict__ tile_cnt, const int64_t* __restrict__ row_off, int64_t N,
-                  int Pc, int bw, int ldw, double* __restrict__ A, double* __restrict__ bc,
-                  double* __restrict__ D, double* __restrict__ E, double* __restrict__ W) {
-    using Cfg = K2ScalarCfg<P>;
-    constexpr int LDT = Cfg::LDT;
-    extern __shared__ double s_mem[];
-    double* s_J = s_mem;                                        // [2*(P+1)][LDT]
-    int* s_span = reinterpret_cast<int*>(s_mem + (size_t)2 * (P + 1) * LDT);
-    int* s_rstart = s_span + TILE_DET;                          // [TILE_DET + 1]
-    int* s_rg = s_rstart + TILE_DET + 1;                        // [TILE_DET]
-    int* s_kb = s_rg + TILE_DET;                                // [TILE_DET][4] super-block of slot m (-1: none)
-    int* s_row = s_kb + 4 * TILE_DET;                           // [TILE_DET][4] global row kb*q + 3*local
-    int* s_misc = s_row + 4 * TILE_DET;                         // [0] = number of runs, [1..4] warp counts
-    const int tl = blockIdx.x, cam = tile_cam[tl], cnt = tile_cnt[tl];
-    const int64_t d0 = tile_start[tl];
-    const int q = 3 * bw;
-    const int tid = threadIdx.x;
-    // ---- stage: planes 0..P-1 = u row, P = r_u, P+1..2P = v row, 2P+1 = r_v (coalesced plane reads)
-    {
-        const int t = tid & (TILE_DET - 1), p0 = tid >> 7;
-        const bool in = t < cnt;
-        const int64_t r0 = row_off[cam], ncam = (row_off[cam + 1] - r0) >> 1;
-        const int64_t loc = d0 + t - (r0 >> 1);
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const double* src = J + (int64_t)(half * P + p0) * N + d0 + t;
-            double* dst = s_J + (half * (P + 1) + p0) * LDT + t;
-#pragma unroll 6
-            for (int p = p0; p < P; p += 2) {
-                *dst = in ? __ldcs(src) : 0.0;
-                src += 2 * N;
-                dst += 2 * LDT;
-            }
-            if (p0 == (P & 1)) s_J[(half * (P + 1) + P) * LDT + t] = in ? r[r0 + half * ncam + loc] : 0.0;
-        }
-    }
-    if (tid < TILE_DET) s_span[tid] = tid < cnt ? span[d0 + tid] : -2;
-    __syncthreads();
-    // ---- run table: maximal runs of equal span index (ballot scan over the 128 tile slots)
-    if (tid < TILE_DET) {
-        const int g = s_span[tid];
-        const bool head = tid < cnt && (tid == 0 || g != s_span[tid - 1]);
-        const unsigned bal = __ballot_sync(0xffffffffu, head);
-        if ((tid & 31) == 0) s_misc[1 + (tid >> 5)] = __popc(bal);
-        s_rg[tid] = head ? (int)(__popc(bal & ((1u << (tid & 31)) - 1u))) : -1;   // rank inside the warp
-    }
-    __syncthreads();
-    if (tid < TILE_DET) {
-        int base = 0;
-        for (int w = 0; w < (tid >> 5); ++w) base += s_misc[1 + w];
-        const int rk = s_rg[tid];
-        const int g = s_span[tid];
-        __syncwarp();
-        if (tid == 0) s_misc[0] = s_misc[1] + s_misc[2] + s_misc[3] + s_misc[4];
-        if (rk >= 0) {
-            s_rstart[base + rk] = tid;
-            s_kb[(base + rk) * 4] = g;     // stash g; expanded after the barrier
-        }
-    }
-    __syncthreads();
-    const int nruns = s_misc[0];
-    if (tid == 0) s_rstart[nruns] = cnt;
-    if (tid < nruns) {
-        const int g = s_kb[tid * 4];
-        s_rg[tid] = g;
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            const int j = g - 3 + m;
-            int kb = -1, row = 0;
-            if (g >= 0 && j >= 0) { kb = j / bw; row = kb * q + (j - kb * bw) * 3; }
-            s_kb[tid * 4 + m] = kb;
-            s_row[tid * 4 + m] = row;
-        }
-    }
-    __syncthreads();
-
-    // ---- per-thread entry constants
-    int typ[Cfg::EPT], sa[Cfg::EPT], sb[Cfg::EPT], xa[Cfg::EPT], xb[Cfg::EPT];
-    const double* pa[Cfg::EPT];
-    const double* pb[Cfg::EPT];
-    double cacc[Cfg::EPT];
-#pragma unroll
-    for (int k = 0; k < Cfg::EPT; ++k) {
-        int e = tid + k * Cfg::THREADS;
-        typ[k] = K2_NONE; sa[k] = 0; sb[k] = 0; xa[k] = 0; xb[k] = 0; cacc[k] = 0.0;
-        pa[k] = s_J; pb[k] = s_J;
-        if (e < Cfg::NE) {
-            // Entry enumeration chosen for coalescing: camera x control entries are ordered
-            // control-row-major, so 9 (18) consecutive lanes RED into contiguous columns of ONE W~ row
-            // (72 B = 3 sectors instead of 9 rows) and share their control operand in shared memory;
-            // control x control entries are row-major in the 12 x 12 block.
-            const int nCC = Pc * 12;                       // camera x control
-            int a, b;
-            if (e < nCC) { b = Pc + e / Pc; a = e - (e / Pc) * Pc; }
-            else if (e < nCC + 12) { a = Pc + (e - nCC); b = P; }                         // control x residual
-            else if (e < nCC + 12 + 78) {                                                 // control x control, la <= lb
-                int t = e - nCC - 12, ra = 0;
-                while (t >= 12 - ra) { t -= 12 - ra; ++ra; }
-                a = Pc + ra; b = Pc + ra + t;
-            } else {                                                                       // camera x camera / residual
-                int t = e - nCC - 12 - 78, ra = 0;
-                while (t >= Pc + 1 - ra) { t -= Pc + 1 - ra; ++ra; }
-                a = ra; b = ra + t;
-                if (b == Pc) b = P;                        // last column of that triangle = residual
-                if (a == Pc) { a = P; b = P; }             // residual x residual (cost; not accumulated)
-            }
-            pa[k] = s_J + a * LDT; pb[k] = s_J + b * LDT;
-            if (a < Pc) {
-                if (b < Pc) { typ[k] = K2_CAMCAM; xa[k] = a; xb[k] = b; }
-                else if (b == P) { typ[k] = K2_CAMRES; xa[k] = a; }
-                else { typ[k] = K2_CAMCTRL; sb[k] = (b - Pc) / 3; xb[k] = (b - Pc) - 3 * sb[k]; xa[k] = cam * Pc + a; }
-            } else if (a < P) {
-                sa[k] = (a - Pc) / 3; xa[k] = (a - Pc) - 3 * sa[k];
-                if (b == P) typ[k] = K2_CTRLRES;
-                else { typ[k] = K2_CTRLCTRL; sb[k] = (b - Pc) / 3; xb[k] = (b - Pc) - 3 * sb[k]; }
-            }
-        }
-    }
-    constexpr int VOFF = (P + 1) * LDT;
-    for (int rr = 0; rr < nruns; ++rr) {
-        if (s_rg[rr] < 0) continue;              // uncovered detections: zero rows
-        const int t0 = s_rstart[rr], t1 = s_rstart[rr + 1];
-#pragma unroll
-        for (int k = 0; k < Cfg::EPT; ++k) {
-            double s = 0.0;
-            const double* qa = pa[k] + t0;
-            const double* qb = pb[k] + t0;
-            int n = t1 - t0;
-#pragma unroll 1
-            for (; n >= 4; n -= 4, qa += 4, qb += 4) {
-                s = fma(qa[0], qb[0], fma(qa[VOFF], qb[VOFF], s));
-                s = fma(qa[1], qb[1], fma(qa[VOFF + 1], qb[VOFF + 1], s));
-                s = fma(qa[2], qb[2], fma(qa[VOFF + 2], qb[VOFF + 2], s));
-                s = fma(qa[3], qb[3], fma(qa[VOFF + 3], qb[VOFF + 3], s));
-            }
-#pragma unroll 1
-            for (; n > 0; --n, ++qa, ++qb) s = fma(qa[0], qb[0], fma(qa[VOFF], qb[VOFF], s));
-            const int ty = typ[k];
-            if (ty <= K2_CAMRES) { cacc[k] += s; continue; }
-            if (s == 0.0) continue;
-            const int kbb = s_kb[rr * 4 + sb[k]];
-            if (ty == K2_CAMCTRL) {
-                if (kbb >= 0) atomicAdd(W + (int64_t)(s_row[rr * 4 + sb[k]] + xb[k]) * ldw + xa[k], s);
-            } else {
-                const int kba = s_kb[rr * 4 + sa[k]];
-                if (kba < 0) continue;
-                const int ra = s_row[rr * 4 + sa[k]] + xa[k];
-                if (ty == K2_CTRLRES) { atomicAdd(W + (int64_t)ra * ldw + (ldw - 1), -s); continue; }
-                if (kbb < 0) continue;
-                const int rb = s_row[rr * 4 + sb[k]] + xb[k];
-                if (kba == kbb) {
-                    atomicAdd(D + (int64_t)ra * q + (rb - kbb * q), s);
-                    if (ra != rb) atomicAdd(D + (int64_t)rb * q + (ra - kba * q), s);
-                } else {
-                    atomicAdd(E + (int64_t)ra * q + (rb - kbb * q), s);
-                }
-            }
-        }
-    }
-    // camera-only entries: once per tile
-#pragma unroll
-    for (int k = 0; k < Cfg::EPT; ++k) {
-        const double v = cacc[k];
-        if (v == 0.0) continue;
-        if (typ[k] == K2_CAMCAM) {
-            atomicAdd(A + ((int64_t)cam * Pc + xa[k]) * Pc + xb[k], v);
-            if (xa[k] != xb[k]) atomicAdd(A + ((int64_t)cam * Pc + xb[k]) * Pc + xa[k], v);
-        } else if (typ[k] == K2_CAMRES) {
-            atomicAdd(bc + cam * Pc + xa[k], -v);
-        }
-    }
-}
-
 // K2m: motion rows -> spline block only.  One thread per sample.
 __global__ void accumulate_motion_kernel(const double* __restrict__ r_motion, const int* __restrict__ mbase,
                                          const double* __restrict__ mJ, int64_t M, int bw, int ldw,
@@ -256,8 +53,7 @@ __global__ void accumulate_motion_kernel(const double* __restrict__ r_motion, co
                     const double v = v1 * fc[k2] * fa[a2];
                     const int l2 = (j2 - kb2 * bw) * 3 + a2;
                     if (kb1 == kb2) {
-                        atomicAdd(D + ((int64_t)kb1 * q + l1) * q + l2, v);
-                        if (l1 != l2) atomicAdd(D + ((int64_t)kb1 * q + l2) * q + l1, v);
+                        atomicAdd(D + ((int64_t)kb1 * q + l1) * q + l2, v);      // l1 <= l2: upper triangle
                     } else {
                         atomicAdd(E + ((int64_t)kb1 * q + l1) * q + l2, v);
                     }
@@ -295,9 +91,9 @@ __global__ void damp_copy_kernel(const double* __restrict__ D, const double* __r
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over nb*q*q
     if (i >= nbq * q) return;
     const int64_t row = i / q;
-    const int col = (int)(i - row * q);
-    double v = D[i];
-    if ((int)(row % q) == col) v = row < n_ctrl3 ? v + lam * diag_s[row] : 1.0;
+    const int col = (int)(i - row * q), l = (int)(row % q);
+    double v = l <= col ? D[i] : D[(row - l + col) * q + l];      // D holds its upper triangle (K2, K2m)
+    if (l == col) v = row < n_ctrl3 ? v + lam * diag_s[row] : 1.0;
     Dw[i] = v;
 }
 
@@ -923,6 +719,8 @@ inline int solver_alloc(mvus_ba_ctx* h) {
     const size_t qq = (size_t)h->q * h->q;
     MV_CUDA(h, h->A.alloc((size_t)h->nc * h->Pc * h->Pc + h->ncP));      // A then bc
     const size_t nba = (size_t)h->nb + 1;                      // +1: ghost block of the sharded solve
+    if ((int64_t)nba * h->q >= ((int64_t)1 << 26))             // K2's run table packs (row << 5 | local column)
+        return fail(h, MVUS_ERR_UNSUPPORTED, "more than 2^26 spline unknowns per handle");
     MV_CUDA(h, h->D.alloc(nba * qq));
     MV_CUDA(h, h->E.alloc(nba * qq));
     MV_CUDA(h, h->W.alloc(nba * h->q * h->ldw));
@@ -958,20 +756,7 @@ inline int accumulate(mvus_ba_ctx* h) {
     MV_CUDA(h, cudaMemsetAsync(h->E.p, 0, h->nb * qq * sizeof(double), h->st));
     MV_CUDA(h, cudaMemsetAsync(h->W.p, 0, (size_t)h->nb * h->q * h->ldw * sizeof(double), h->st));
     if (h->n_tiles > 0) {
-        static const bool scalar_k2 = [] { const char* e = getenv("MVUS_BA_K2"); return e && !strcmp(e, "scalar"); }();
-        if (scalar_k2) {
-            if (h->P == 21) {
-                MV_CUDA(h, cudaFuncSetAttribute(accumulate_scalar_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2ScalarCfg<21>::SMEM));
-                accumulate_scalar_kernel<21><<<h->n_tiles, 256, K2ScalarCfg<21>::SMEM, h->st>>>(
-                    h->J.p, h->r.p, h->span.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
-                    h->Pc, h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
-            } else {
-                MV_CUDA(h, cudaFuncSetAttribute(accumulate_scalar_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2ScalarCfg<30>::SMEM));
-                accumulate_scalar_kernel<30><<<h->n_tiles, 256, K2ScalarCfg<30>::SMEM, h->st>>>(
-                    h->J.p, h->r.p, h->span.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
-                    h->Pc, h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
-            }
-        } else if (h->P == 21) {
+        if (h->P == 21) {
             MV_CUDA(h, cudaFuncSetAttribute(accumulate_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2Cfg<21>::SMEM));
             accumulate_kernel<21><<<h->n_tiles, K2Cfg<21>::THREADS, K2Cfg<21>::SMEM, h->st>>>(
                 h->J.p, h->r.p, h->span.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,

@@ -647,7 +647,8 @@ extern "C" int mvus_ba_normal_equations(mvus_ba_handle h, const double* x, doubl
                     for (int a = 0; a < 3; ++a)
                         for (int b = 0; b < 3; ++b) {
                             const int la = (int)(i - ki * bw) * 3 + a, lb = (int)(j - kj * bw) * 3 + b;
-                            const double v = (ki == kj) ? D[((size_t)ki * q + la) * q + lb] : E[((size_t)ki * q + la) * q + lb];
+                            const double v = (ki == kj) ? D[((size_t)ki * q + std::min(la, lb)) * q + std::max(la, lb)]   // upper triangle stored
+                                                    : E[((size_t)ki * q + la) * q + lb];
                             Hss[((size_t)i * band + dj) * 9 + a * 3 + b] = v;
                         }
                 }
