@@ -81,6 +81,8 @@ struct mvus_ba_ctx {
     // per-evaluation state
     mvus::DevBuf<double> x, x_trial, camprep, r, J, mJ, partial, scratch, gt_out;
     mvus::DevBuf<int> span, mbase, flag, frozen;
+    mvus::DevBuf<int> tile_key, tile_key2, tile_id, tile_perm;   // K2 tile order (by first span index)
+    mvus::DevBuf<unsigned char> sort_tmp;
     double* h_pin = nullptr;      // pinned scratch for scalars
     size_t h_pin_n = 0;
 

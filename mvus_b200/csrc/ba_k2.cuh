@@ -6,16 +6,21 @@
 //   * the k dimension packs the run's u rows followed by its v rows (2 n rows, 4 per MMA step),
 //   * every tile pair (i <= j) is one 8x8 accumulator fragment; lane (fm = lane>>2, fk = lane&3)
 //     holds C[8 i + fm][8 j + 2 fk + e], e = 0, 1.
-// Entries whose column is a control point are flushed at the end of the run with predicated FP64
-// REDs (camera x control -> W~ with the 8 lanes of equal fk writing 8 consecutive columns of one
-// row; control x control -> E, or the UPPER triangle of D: damp_copy_kernel mirrors it);
-// camera-only entries stay in registers for the whole tile, are summed over the CTA's warps
-// through shared memory and written once per tile.
+// A warp owns a contiguous chunk of the tile (16 detections, ~3 runs at config 4) and keeps a
+// SLIDING WINDOW over the control points: control point j always lives in column slot j mod 4,
+// so consecutive runs (spans g, g+1, ...) share three of their four slots and only the slot
+// whose control point leaves the window is flushed (predicated FP64 REDs: camera x control ->
+// W~, the 8 lanes of equal fk writing 8 consecutive columns of one row; control x control -> E
+// or the UPPER triangle of D, damp_copy_kernel mirrors it) -- the L2 atomic units, not the SMs,
+// bound this kernel (measured: 11 of 22 ms at config 4 with one flush per run).  Camera-only
+// entries stay in registers for the whole tile, are summed over the CTA's warps through shared
+// memory and written once per tile.
 // Against the scalar version (one thread per entry, 4 shared loads per 2 FMAs, bound by
 // shared-memory bandwidth) a run of 5 detections costs 9 shared loads + 18 MMAs per warp.
 // HBM traffic per detection (algorithmic): read r (16 B) + span (4 B) + J (16 P B)
 //   -> 356 B (P=21) / 500 B (P=30); writes are O(runs), not O(detections).
 #pragma once
+#include <cub/cub.cuh>
 #include "ba_ctx.cuh"
 
 namespace mvus {
@@ -33,11 +38,11 @@ struct K2Cfg {
     static constexpr int NKEEP = (TR + 1) * (TR + 2) / 2;   // tile pairs with camera-only entries
     static constexpr int THREADS = 256, WARPS = THREADS / 32;
     static constexpr int LDT = TILE_DET + 4;           // +4: conflict-free fragment loads (4 fm + fk pattern)
-    static constexpr int SPLIT = 16;                   // forced run split when a tile has few runs
+    static constexpr int CHUNK = TILE_DET / WARPS;     // detections per warp; runs are cut at chunk boundaries
     static constexpr int CT = 8 * NCT;                 // run-table entries per run: position in the control tiles
     // staged planes + span + run start + run span + per-run control-column table + misc
     static constexpr size_t SMEM = (size_t)(2 * (P + 1)) * LDT * sizeof(double) +
-                                   (size_t)(TILE_DET + (TILE_DET + 1) + TILE_DET + CT * TILE_DET + 8) * sizeof(int);
+                                   (size_t)(TILE_DET + (TILE_DET + 1) + TILE_DET + CT * TILE_DET + TILE_DET + 16 + 8) * sizeof(int);
     static_assert(8 * TC <= PC, "row tiles below TC must hold camera columns only");
     static_assert(TC == TR, "the residual slot must sit in the first control tile");
     static_assert((size_t)WARPS * NKEEP * 64 <= (size_t)(2 * (P + 1)) * LDT, "partial sums must fit the staging area");
@@ -78,11 +83,22 @@ __device__ __forceinline__ constexpr unsigned k2_rowbits(int ii) {
     return bits;
 }
 
+// Tile order of K2: by the span index of the tile's first detection, i.e. by TIME across all cameras.
+// Tiles that run concurrently then update the same few hundred control points: the D / E blocks and
+// W~ rows they RED into stay in L2 (in camera-major order every camera's sweep re-fetched all of D, E
+// and its 72-byte segments of every W~ row from DRAM: 14 GB read + 10 GB written at config 4).
+__global__ void tile_key_kernel(const int* __restrict__ span, const int64_t* __restrict__ tile_start,
+                                int n_tiles, int* __restrict__ key, int* __restrict__ id) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tiles) { key[i] = span[tile_start[i]]; id[i] = i; }
+}
+
 template <int P>
 __global__ void __launch_bounds__(256, (P == 21 ? 4 : 3))
 accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, const int* __restrict__ span,
-                  const int* __restrict__ tile_cam, const int64_t* __restrict__ tile_start,
-                  const int* __restrict__ tile_cnt, const int64_t* __restrict__ row_off, int64_t N,
+                  const int* __restrict__ tile_perm, const int* __restrict__ tile_cam,
+                  const int64_t* __restrict__ tile_start, const int* __restrict__ tile_cnt,
+                  const int64_t* __restrict__ row_off, int64_t N,
                   int bw, int ldw, double* __restrict__ A, double* __restrict__ bc,
                   double* __restrict__ D, double* __restrict__ E, double* __restrict__ W) {
     using Cfg = K2Cfg<P>;
@@ -97,8 +113,10 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
     int* s_ctab = s_rg + TILE_DET;                              // [TILE_DET][CT] (global row << 5 | local column) of
                                                                 //   the control column at position x of the control
                                                                 //   tiles, -1 if that position is no control point
-    int* s_misc = s_ctab + CT * TILE_DET;                       // [0] = number of runs, [1..4] warp counts, [5] next run
-    const int tl = blockIdx.x, cam = tile_cam[tl], cnt = tile_cnt[tl];
+    int* s_leave = s_ctab + CT * TILE_DET;                      // [TILE_DET] slots (bit mask) to flush after the run
+    int* s_first = s_leave + TILE_DET;                          // [WARPS + 1] first run of each warp's chunk
+    int* s_misc = s_first + 16;                                 // [0] = number of runs, [1..4] warp counts
+    const int tl = tile_perm[blockIdx.x], cam = tile_cam[tl], cnt = tile_cnt[tl];
     const int64_t d0 = tile_start[tl];
     const int q = 3 * bw;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -126,13 +144,9 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     if (tid < TILE_DET) s_span[tid] = tid < cnt ? span[d0 + tid] : -2;
-    if (tid == 0) s_misc[5] = Cfg::WARPS;                       // runs 0..WARPS-1 are taken statically
     __syncthreads();
-    // ---- run table: maximal runs of equal span index; a tile with few runs is additionally cut
-    //      every SPLIT slots so that all warps have work (the partial sums simply add up)
-    bool head = tid < cnt && (tid == 0 || s_span[tid] != s_span[tid - 1]);
-    const int natural = __syncthreads_count(head);
-    if (natural < 12) head = head || (tid < cnt && (tid & (Cfg::SPLIT - 1)) == 0);
+    // ---- run table: runs of equal span index, cut at the boundaries of the warps' chunks
+    const bool head = tid < cnt && (tid == 0 || s_span[tid] != s_span[tid - 1] || (tid & (Cfg::CHUNK - 1)) == 0);
     if (tid < TILE_DET) {
         const unsigned bal = __ballot_sync(0xffffffffu, head);
         if (lane == 0) s_misc[1 + warp] = __popc(bal);
@@ -156,31 +170,66 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
     __syncthreads();
     const int nruns = s_misc[0];
     if (tid == 0) s_rstart[nruns] = cnt;
+    // control point j lives in slot j & 3: position x = CPAD + 3 slot + axis holds, for a run of span g,
+    // the control point j = g - ((g - slot) & 3) of its window g-3 .. g
     for (int x = tid; x < nruns * CT; x += Cfg::THREADS) {
-        const int g = s_rg[x / CT], cb = x % CT - CPAD;         // control column 0..11 of the run's 4 x 3 window
+        const int g = s_rg[x / CT], cb = x % CT - CPAD;
         int packed = -1;
         if (g >= 0 && cb >= 0 && cb < 12) {
-            const int m = cb / 3, j = g - 3 + m;
+            const int sl = cb / 3, j = g - ((g - sl) & 3);
             if (j >= 0) {
-                const int kb = j / bw, lc = (j - kb * bw) * 3 + (cb - 3 * m);
+                const int kb = j / bw, lc = (j - kb * bw) * 3 + (cb - 3 * sl);
                 packed = ((kb * q + lc) << 5) | lc;
             }
         }
         s_ctab[x] = packed;
     }
+    __syncthreads();                                            // s_rstart complete
+    // slots to flush after a run: those whose control point differs in the next run of the same warp
+    // (all four at the end of the warp's chunk or before uncovered detections)
+    if (tid < nruns) {
+        const int g = s_rg[tid], nx = tid + 1;
+        int leave = 0xF;
+        if (nx < nruns && (s_rstart[nx] / Cfg::CHUNK) == (s_rstart[tid] / Cfg::CHUNK) && s_rg[nx] >= 0 && g >= 0) {
+            const int gn = s_rg[nx];
+            leave = 0;
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl)
+                if (g - ((g - sl) & 3) != gn - ((gn - sl) & 3)) leave |= 1 << sl;
+        }
+        s_leave[tid] = leave;
+    }
+    // first run of each warp's chunk = number of run heads before slot CHUNK * w
+    if (tid <= Cfg::WARPS) {
+        int lo = 0, hi = nruns;                                 // first run with start >= CHUNK * tid
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_rstart[mid] < Cfg::CHUNK * tid) lo = mid + 1; else hi = mid;
+        }
+        s_first[tid] = tid == Cfg::WARPS ? nruns : lo;
+    }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
 
-    // ---- one warp per run
+    // ---- one warp per chunk of CHUNK detections, run by run
     const int fk = lane & 3, fm = lane >> 2;
-    int pl[NT];                                   // staged plane (in doubles) of slot 8 i + fm, -1 = padding
+    int pl[NT];                                   // staged plane (in doubles) of slot 8 i + fm, -1 = padding;
+                                                  //   control slots: plane of axis ax in window position 0
+    int psl[NCT];                                 // control slots: slot id 0..3 (else -1)
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
         const int s = 8 * i + fm;
-        pl[i] = s < PC ? s * LDT : (s == PC ? P * LDT : (s <= PC + 12 ? (s - 1) * LDT : -1));
+        pl[i] = s < PC ? s * LDT : (s == PC ? P * LDT : -1);
+        if (i >= TC) {
+            const int cb = s - PC - 1;
+            const bool ok = cb >= 0 && cb < 12;
+            psl[i - TC] = ok ? cb / 3 : -1;
+            if (ok) pl[i] = (PC + cb - 3 * (cb / 3)) * LDT;
+        }
     }
-    // lane constants of the flush: which accumulator entries (bit 2 k + e) this lane can ever flush
-    unsigned vmask = 0;
+    // lane constants of the flush: which accumulator entries (bit 2 k + e) this lane can ever flush, and the
+    // slots they belong to (4-bit sets: columns (jj, e) at bits 4 (2 jj + e), row tiles at bits 16 + 4 ii)
+    unsigned vmask = 0, sbits = 0;
     {
         int k = 0;
 #pragma unroll
@@ -194,6 +243,18 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
                     if (cb >= 0 && cb < 12 && a <= b) vmask |= 1u << (2 * k + e);   // a <= b: never a padding row
                 }
             }
+#pragma unroll
+        for (int jj = 0; jj < NCT; ++jj)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int cb = 8 * jj + 2 * fk + e - CPAD;
+                if (cb >= 0 && cb < 12) sbits |= (1u << (cb / 3)) << (4 * (2 * jj + e));
+            }
+#pragma unroll
+        for (int ii = 0; ii < NCT; ++ii) {
+            const int ca = 8 * ii + fm - CPAD;
+            if (ca >= 0 && ca < 12) sbits |= (1u << (ca / 3)) << (16 + 4 * ii);
+        }
     }
     const bool rW0 = fm < CPAD;                   // this lane's row of tile TC is a camera / residual row (target W~)
     double* const Wc0 = W + cam * PC + fm;        // rows of the camera-only tiles: column cam*PC + 8 i + fm
@@ -203,99 +264,99 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
 #pragma unroll
     for (int k = 0; k < Cfg::NPAIR; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
 
-    int rr = warp;
-    while (rr < nruns) {
-        int rnext = 0;                               // next run: taken from the CTA's counter (balances the warps)
-        if (lane == 0) rnext = atomicAdd(&s_misc[5], 1);
+    const int rr_end = s_first[warp + 1];
+    for (int rr = s_first[warp]; rr < rr_end; ++rr) {
         const int g = s_rg[rr];
-        if (g >= 0) {                                // g < 0: uncovered detections, zero rows
-            const int t0 = s_rstart[rr], n = s_rstart[rr + 1] - t0;
-            const int nsteps = (2 * n + 3) >> 2;
-            double fc[NT], fn[NT];
+        if (g < 0) continue;                         // uncovered detections: zero rows
+        const int t0 = s_rstart[rr], n = s_rstart[rr + 1] - t0;
+        const int nsteps = (2 * n + 3) >> 2;
+        int plr[NT];                                 // planes of this run: window position of slot sl is (sl - g - 1) & 3
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            plr[i] = pl[i];
+            if (i >= TC && psl[i - TC] >= 0) plr[i] = pl[i] + ((psl[i - TC] - g - 1) & 3) * (3 * LDT);
+        }
+        double fc[NT], fn[NT];
+        {
+            const int rho = fk;
+            const bool hv = rho >= n;
+            const int off = t0 + rho + (hv ? VOFF - n : 0);
+            const bool ok = rho < 2 * n;
+#pragma unroll
+            for (int i = 0; i < NT; ++i) fc[i] = (ok && plr[i] >= 0) ? s_J[plr[i] + off] : 0.0;
+        }
+#pragma unroll 1
+        for (int s = 0; s < nsteps; ++s) {
             {
-                const int rho = fk;
+                const int rho = 4 * (s + 1) + fk;
                 const bool hv = rho >= n;
                 const int off = t0 + rho + (hv ? VOFF - n : 0);
                 const bool ok = rho < 2 * n;
 #pragma unroll
-                for (int i = 0; i < NT; ++i) fc[i] = (ok && pl[i] >= 0) ? s_J[pl[i] + off] : 0.0;
-            }
-#pragma unroll 1
-            for (int s = 0; s < nsteps; ++s) {
-                {
-                    const int rho = 4 * (s + 1) + fk;
-                    const bool hv = rho >= n;
-                    const int off = t0 + rho + (hv ? VOFF - n : 0);
-                    const bool ok = rho < 2 * n;
-#pragma unroll
-                    for (int i = 0; i < NT; ++i) fn[i] = (ok && pl[i] >= 0) ? s_J[pl[i] + off] : 0.0;
-                }
-                int k = 0;
-#pragma unroll
-                for (int i = 0; i < NT; ++i)
-#pragma unroll
-                    for (int j = i; j < NT; ++j, ++k) k2_dmma(acc[k][0], acc[k][1], fc[i], fc[j]);
-#pragma unroll
-                for (int i = 0; i < NT; ++i) fc[i] = fn[i];
-            }
-            // ---- flush the entries whose column is a control point (slots PC+1 .. PC+12).  Addresses are
-            //      (row pointer) + (column offset): both are set up once per run, an entry costs a select,
-            //      an address add and the predicated RED.  D receives its upper triangle only.
-            const int* ct = s_ctab + rr * CT;
-            unsigned m = vmask;
-            int64_t cw[NCT][2];                      // W~: row offset (row * ldw) of the column's control row
-            int ccl[NCT][2], cblk[NCT][2];           // D / E: local column, first row of the super-block
-#pragma unroll
-            for (int jj = 0; jj < NCT; ++jj)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int pk = ct[8 * jj + 2 * fk + e];
-                    const int rb = pk >> 5;
-                    cw[jj][e] = (int64_t)rb * ldw;
-                    ccl[jj][e] = pk & 31;
-                    cblk[jj][e] = rb - (pk & 31);
-                    if (pk < 0) m &= ~k2_colbits<NT, TC>(jj, e);
-                }
-            double* pd[NCT];                         // row pointers: D / E row of a control row, W~ column of a camera row
-            double* pe[NCT];
-            int ablk[NCT];
-#pragma unroll
-            for (int ii = 0; ii < NCT; ++ii) {
-                const int pk = ct[8 * ii + fm];
-                const int ra = pk >> 5;
-                const bool rw = ii == 0 && rW0;
-                ablk[ii] = ra - (pk & 31);
-                pd[ii] = rw ? Wr0 : D + (int64_t)ra * q;
-                pe[ii] = rw ? Wr0 : E + (int64_t)ra * q;
-                if (!rw && pk < 0) m &= ~k2_rowbits<NT, TC>(ii);
+                for (int i = 0; i < NT; ++i) fn[i] = (ok && plr[i] >= 0) ? s_J[plr[i] + off] : 0.0;
             }
             int k = 0;
 #pragma unroll
-            for (int i = 0; i < NT; ++i) {
+            for (int i = 0; i < NT; ++i)
 #pragma unroll
-                for (int j = i; j < NT; ++j, ++k) {
-                    if (j < TC) continue;            // camera-only tile pair: stays in registers
+                for (int j = i; j < NT; ++j, ++k) k2_dmma(acc[k][0], acc[k][1], fc[i], fc[j]);
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const double v = acc[k][e];
-                        if (j > TR) acc[k][e] = 0.0;
-                        else if (2 * fk + e >= CPAD) acc[k][e] = 0.0;    // j == TR == TC: control column
-                        const bool pred = ((m >> (2 * k + e)) & 1u) && v != 0.0;
-                        if (i < TC) {                // camera rows only
-                            k2_red(Wc0 + 8 * i + cw[j - TC][e], v, pred);
-                        } else {
-                            const int ii = i - TC;
-                            const bool rw = ii == 0 && rW0;
-                            double* base = ablk[ii] == cblk[j - TC][e] ? pd[ii] : pe[ii];
-                            const int64_t off = rw ? cw[j - TC][e] : (int64_t)ccl[j - TC][e];
-                            const double val = ii == 0 ? __hiloint2double(__double2hiint(v) ^ flip0, __double2loint(v)) : v;
-                            k2_red(base + off, val, pred);
-                        }
+            for (int i = 0; i < NT; ++i) fc[i] = fn[i];
+        }
+        // ---- flush the entries of the slots that leave the window (all at the end of the chunk).
+        //      Addresses are (row pointer) + (column offset), set up once per flush; an entry costs a few
+        //      selects, an address add and the predicated RED.  D receives its upper triangle only.
+        const unsigned lm = (unsigned)s_leave[rr];
+        if (lm == 0) continue;
+        const int* ct = s_ctab + rr * CT;
+        unsigned m = vmask;
+        int cpk[NCT][2];                             // packed (row << 5 | local column) of the lane's columns
+#pragma unroll
+        for (int jj = 0; jj < NCT; ++jj)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                cpk[jj][e] = ct[8 * jj + 2 * fk + e];
+                if (cpk[jj][e] < 0) m &= ~k2_colbits<NT, TC>(jj, e);
+            }
+        int apk[NCT];                                // the same for the lane's rows in the control tiles
+#pragma unroll
+        for (int ii = 0; ii < NCT; ++ii) {
+            apk[ii] = ct[8 * ii + fm];
+            if (!(ii == 0 && rW0) && apk[ii] < 0) m &= ~k2_rowbits<NT, TC>(ii);
+        }
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+#pragma unroll
+            for (int j = i; j < NT; ++j, ++k) {
+                if (j < TC) continue;                // camera-only tile pair: stays in registers
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int jj = j - TC;
+                    unsigned em = sbits >> (4 * (2 * jj + e));
+                    if (i >= TC) em |= sbits >> (16 + 4 * (i - TC));
+                    const bool go = (em & lm & 0xFu) != 0;        // one of the entry's slots leaves
+                    const double v = acc[k][e];
+                    if (go) acc[k][e] = 0.0;                       // (camera-only entries have no slot: kept)
+                    const bool pred = go && ((m >> (2 * k + e)) & 1u) && v != 0.0;
+                    const int pb = cpk[jj][e];
+                    if (i < TC) {                    // camera rows only
+                        k2_red(Wc0 + 8 * i + (int64_t)(pb >> 5) * ldw, v, pred);
+                    } else {
+                        const int ii = i - TC;
+                        const bool rw = ii == 0 && rW0;
+                        const int pa = apk[ii];
+                        // control x control: (row, column) ordered by control point (slots rotate)
+                        const int pr = pa <= pb ? pa : pb, pc = pa <= pb ? pb : pa;
+                        const bool same = (pr >> 5) - (pr & 31) == (pc >> 5) - (pc & 31);
+                        double* ptr = rw ? Wr0 + (int64_t)(pb >> 5) * ldw
+                                         : (same ? D : E) + (int64_t)(pr >> 5) * q + (pc & 31);
+                        const double val = ii == 0 ? __hiloint2double(__double2hiint(v) ^ flip0, __double2loint(v)) : v;
+                        k2_red(ptr, val, pred);
                     }
                 }
             }
         }
-        rr = __shfl_sync(0xffffffffu, rnext, 0);
     }
 
     // ---- camera-only entries: sum the warps' fragments through shared memory, one RED per tile

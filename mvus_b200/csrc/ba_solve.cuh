@@ -756,15 +756,29 @@ inline int accumulate(mvus_ba_ctx* h) {
     MV_CUDA(h, cudaMemsetAsync(h->E.p, 0, h->nb * qq * sizeof(double), h->st));
     MV_CUDA(h, cudaMemsetAsync(h->W.p, 0, (size_t)h->nb * h->q * h->ldw * sizeof(double), h->st));
     if (h->n_tiles > 0) {
+        // tile order by time (see tile_key_kernel); spans move little between evaluations, but the sort is cheap
+        const int nt = h->n_tiles;
+        MV_CUDA(h, h->tile_key.alloc(nt));
+        MV_CUDA(h, h->tile_key2.alloc(nt));
+        MV_CUDA(h, h->tile_id.alloc(nt));
+        MV_CUDA(h, h->tile_perm.alloc(nt));
+        size_t tb = 0;
+        MV_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, h->tile_key.p, h->tile_key2.p, h->tile_id.p,
+                                                   h->tile_perm.p, nt, 0, 32, h->st));
+        MV_CUDA(h, h->sort_tmp.alloc(tb));
+        tile_key_kernel<<<(nt + 255) / 256, 256, 0, h->st>>>(h->span.p, h->tile_start.p, nt, h->tile_key.p, h->tile_id.p);
+        MV_CUDA(h, cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tb, h->tile_key.p, h->tile_key2.p, h->tile_id.p,
+                                                   h->tile_perm.p, nt, 0, 32, h->st));
+        h->launches += 3;
         if (h->P == 21) {
             MV_CUDA(h, cudaFuncSetAttribute(accumulate_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2Cfg<21>::SMEM));
             accumulate_kernel<21><<<h->n_tiles, K2Cfg<21>::THREADS, K2Cfg<21>::SMEM, h->st>>>(
-                h->J.p, h->r.p, h->span.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
+                h->J.p, h->r.p, h->span.p, h->tile_perm.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
                 h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
         } else {
             MV_CUDA(h, cudaFuncSetAttribute(accumulate_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2Cfg<30>::SMEM));
             accumulate_kernel<30><<<h->n_tiles, K2Cfg<30>::THREADS, K2Cfg<30>::SMEM, h->st>>>(
-                h->J.p, h->r.p, h->span.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
+                h->J.p, h->r.p, h->span.p, h->tile_perm.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
                 h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
         }
         h->launches++;

@@ -83,9 +83,10 @@ extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
         b->release();
     for (auto* b : {&h->row_off, &h->tile_start, &h->knot_off, &h->ctrl_off, &h->xoff, &h->lut_off}) b->release();
     for (auto* b : {&h->tile_cam, &h->tile_cnt, &h->ncoef, &h->deg, &h->lut_n, &h->lut, &h->tau_spl, &h->span,
-                    &h->mbase, &h->flag, &h->frozen})
+                    &h->mbase, &h->flag, &h->frozen, &h->tile_key, &h->tile_key2, &h->tile_id, &h->tile_perm})
         b->release();
     h->tau_flag.release();
+    h->sort_tmp.release();
     if (h->h_pin) cudaFreeHost(h->h_pin);
     for (int k = 0; k < 8; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     if (h->st) cudaStreamDestroy(h->st);
