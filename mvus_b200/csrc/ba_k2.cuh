@@ -25,6 +25,8 @@
 
 namespace mvus {
 
+constexpr int K2_TILE = TILE_DET;      // 64 measured the same (15.5 vs 15.4 ms at config 4)
+
 template <int P>
 struct K2Cfg {
     static constexpr int PC = P - 12;                  // camera unknowns (9 or 18)
@@ -36,13 +38,15 @@ struct K2Cfg {
     static constexpr int NCT = NT - TC;                // tiles with control slots
     static constexpr int CPAD = PC + 1 - 8 * TC;       // camera-side slots at the start of tile TC
     static constexpr int NKEEP = (TR + 1) * (TR + 2) / 2;   // tile pairs with camera-only entries
-    static constexpr int THREADS = 256, WARPS = THREADS / 32;
-    static constexpr int LDT = TILE_DET + 4;           // +4: conflict-free fragment loads (4 fm + fk pattern)
-    static constexpr int CHUNK = TILE_DET / WARPS;     // detections per warp; runs are cut at chunk boundaries
+    static constexpr int KT = K2_TILE;                 // detections per CTA (a K1 tile is cut into TILE_DET / KT parts)
+    static constexpr int SPLITS = TILE_DET / KT;
+    static constexpr int THREADS = 2 * KT, WARPS = THREADS / 32;
+    static constexpr int LDT = KT + 4;           // +4: conflict-free fragment loads (4 fm + fk pattern)
+    static constexpr int CHUNK = KT / WARPS;     // detections per warp; runs are cut at chunk boundaries
     static constexpr int CT = 8 * NCT;                 // run-table entries per run: position in the control tiles
     // staged planes + span + run start + run span + per-run control-column table + misc
     static constexpr size_t SMEM = (size_t)(2 * (P + 1)) * LDT * sizeof(double) +
-                                   (size_t)(TILE_DET + (TILE_DET + 1) + TILE_DET + CT * TILE_DET + TILE_DET + 16 + 8) * sizeof(int);
+                                   (size_t)(KT + (KT + 1) + KT + 12 * KT + 16 + 8) * sizeof(int);
     static_assert(8 * TC <= PC, "row tiles below TC must hold camera columns only");
     static_assert(TC == TR, "the residual slot must sit in the first control tile");
     static_assert((size_t)WARPS * NKEEP * 64 <= (size_t)(2 * (P + 1)) * LDT, "partial sums must fit the staging area");
@@ -94,7 +98,7 @@ __global__ void tile_key_kernel(const int* __restrict__ span, const int64_t* __r
 }
 
 template <int P>
-__global__ void __launch_bounds__(256, (P == 21 ? 4 : 3))
+__global__ void __launch_bounds__(K2Cfg<P>::THREADS, (P == 21 ? 4 : 3) * (256 / K2Cfg<P>::THREADS))
 accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, const int* __restrict__ span,
                   const int* __restrict__ tile_perm, const int* __restrict__ tile_cam,
                   const int64_t* __restrict__ tile_start, const int* __restrict__ tile_cnt,
@@ -103,27 +107,29 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
                   double* __restrict__ D, double* __restrict__ E, double* __restrict__ W) {
     using Cfg = K2Cfg<P>;
     constexpr int NT = Cfg::NT, PC = Cfg::PC, LDT = Cfg::LDT, TR = Cfg::TR, TC = Cfg::TC;
-    constexpr int NCT = Cfg::NCT, CPAD = Cfg::CPAD, CT = Cfg::CT;
+    constexpr int NCT = Cfg::NCT, CPAD = Cfg::CPAD, CT = Cfg::CT, KT = Cfg::KT;
     constexpr int VOFF = (P + 1) * LDT;
     extern __shared__ double s_mem[];
     double* s_J = s_mem;                                        // [2*(P+1)][LDT]: u planes (P = r_u), then v planes
     int* s_span = reinterpret_cast<int*>(s_mem + (size_t)2 * (P + 1) * LDT);
-    int* s_rstart = s_span + TILE_DET;                          // [TILE_DET + 1]
-    int* s_rg = s_rstart + TILE_DET + 1;                        // [TILE_DET] span index of the run
-    int* s_ctab = s_rg + TILE_DET;                              // [TILE_DET][CT] (global row << 5 | local column) of
-                                                                //   the control column at position x of the control
-                                                                //   tiles, -1 if that position is no control point
-    int* s_leave = s_ctab + CT * TILE_DET;                      // [TILE_DET] slots (bit mask) to flush after the run
-    int* s_first = s_leave + TILE_DET;                          // [WARPS + 1] first run of each warp's chunk
+    int* s_rstart = s_span + KT;                                // [KT + 1]
+    int* s_rg = s_rstart + KT + 1;                              // [KT] span index of the run
+    int* s_ctab = s_rg + KT;                                    // [KT][12] (global row << 5 | local column) of the
+                                                                //   run's control column slot*3 + axis, -1 if none
+    int* s_leave = s_span;                                      // [KT] slots (bit mask) to flush after the run
+                                                                //   (aliases s_span, dead once the runs are known)
+    int* s_first = s_ctab + 12 * KT;                          // [WARPS + 1] first run of each warp's chunk
     int* s_misc = s_first + 16;                                 // [0] = number of runs, [1..4] warp counts
-    const int tl = tile_perm[blockIdx.x], cam = tile_cam[tl], cnt = tile_cnt[tl];
-    const int64_t d0 = tile_start[tl];
+    const int tl = tile_perm[blockIdx.x / Cfg::SPLITS], part = blockIdx.x % Cfg::SPLITS, cam = tile_cam[tl];
+    const int cnt = min(tile_cnt[tl] - part * KT, KT);
+    if (cnt <= 0) return;
+    const int64_t d0 = tile_start[tl] + part * KT;
     const int q = 3 * bw;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // ---- stage the tile with 8-byte cp.async (all 2 (P+1) planes of a thread in flight at once;
     //      zero fill past the end of the tile); the run table is built while the copies land
     {
-        const int t = tid & (TILE_DET - 1), p0 = tid >> 7;
+        const int t = tid & (KT - 1), p0 = tid / KT;
         const unsigned sz = t < cnt ? 8u : 0u;
         const int64_t r0 = row_off[cam], ncam = (row_off[cam + 1] - r0) >> 1;
         const int64_t loc = d0 + t - (r0 >> 1);
@@ -143,11 +149,11 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    if (tid < TILE_DET) s_span[tid] = tid < cnt ? span[d0 + tid] : -2;
+    if (tid < KT) s_span[tid] = tid < cnt ? span[d0 + tid] : -2;
     __syncthreads();
     // ---- run table: runs of equal span index, cut at the boundaries of the warps' chunks
     const bool head = tid < cnt && (tid == 0 || s_span[tid] != s_span[tid - 1] || (tid & (Cfg::CHUNK - 1)) == 0);
-    if (tid < TILE_DET) {
+    if (tid < KT) {
         const unsigned bal = __ballot_sync(0xffffffffu, head);
         if (lane == 0) s_misc[1 + warp] = __popc(bal);
         s_rg[tid] = head ? (int)(__popc(bal & ((1u << lane) - 1u))) : -1;          // rank inside the warp
@@ -155,13 +161,17 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
     __syncthreads();
     {
         int rk = -1, g = 0, base = 0;
-        if (tid < TILE_DET) {
+        if (tid < KT) {
             for (int w = 0; w < warp; ++w) base += s_misc[1 + w];
             rk = s_rg[tid];
             g = s_span[tid];
         }
         __syncthreads();                                        // every rank is read before s_rg is rewritten
-        if (tid == 0) s_misc[0] = s_misc[1] + s_misc[2] + s_misc[3] + s_misc[4];
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < KT / 32; ++w) tot += s_misc[1 + w];
+            s_misc[0] = tot;
+        }
         if (rk >= 0) {
             s_rstart[base + rk] = tid;
             s_rg[base + rk] = g;
@@ -172,10 +182,10 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
     if (tid == 0) s_rstart[nruns] = cnt;
     // control point j lives in slot j & 3: position x = CPAD + 3 slot + axis holds, for a run of span g,
     // the control point j = g - ((g - slot) & 3) of its window g-3 .. g
-    for (int x = tid; x < nruns * CT; x += Cfg::THREADS) {
-        const int g = s_rg[x / CT], cb = x % CT - CPAD;
+    for (int x = tid; x < nruns * 12; x += Cfg::THREADS) {
+        const int g = s_rg[x / 12], cb = x % 12;
         int packed = -1;
-        if (g >= 0 && cb >= 0 && cb < 12) {
+        if (g >= 0) {
             const int sl = cb / 3, j = g - ((g - sl) & 3);
             if (j >= 0) {
                 const int kb = j / bw, lc = (j - kb * bw) * 3 + (cb - 3 * sl);
@@ -308,7 +318,8 @@ accumulate_kernel(const double* __restrict__ J, const double* __restrict__ r, co
         //      selects, an address add and the predicated RED.  D receives its upper triangle only.
         const unsigned lm = (unsigned)s_leave[rr];
         if (lm == 0) continue;
-        const int* ct = s_ctab + rr * CT;
+        const int* ct = s_ctab + rr * 12 - CPAD;     // indexed by position in the control tiles; positions that are
+                                                     //   no control column read a neighbour's entry and are masked by vmask
         unsigned m = vmask;
         int cpk[NCT][2];                             // packed (row << 5 | local column) of the lane's columns
 #pragma unroll

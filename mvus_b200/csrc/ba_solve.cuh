@@ -772,12 +772,12 @@ inline int accumulate(mvus_ba_ctx* h) {
         h->launches += 3;
         if (h->P == 21) {
             MV_CUDA(h, cudaFuncSetAttribute(accumulate_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2Cfg<21>::SMEM));
-            accumulate_kernel<21><<<h->n_tiles, K2Cfg<21>::THREADS, K2Cfg<21>::SMEM, h->st>>>(
+            accumulate_kernel<21><<<h->n_tiles * K2Cfg<21>::SPLITS, K2Cfg<21>::THREADS, K2Cfg<21>::SMEM, h->st>>>(
                 h->J.p, h->r.p, h->span.p, h->tile_perm.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
                 h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
         } else {
             MV_CUDA(h, cudaFuncSetAttribute(accumulate_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2Cfg<30>::SMEM));
-            accumulate_kernel<30><<<h->n_tiles, K2Cfg<30>::THREADS, K2Cfg<30>::SMEM, h->st>>>(
+            accumulate_kernel<30><<<h->n_tiles * K2Cfg<30>::SPLITS, K2Cfg<30>::THREADS, K2Cfg<30>::SMEM, h->st>>>(
                 h->J.p, h->r.p, h->span.p, h->tile_perm.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
                 h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
         }
