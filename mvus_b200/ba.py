@@ -281,6 +281,7 @@ def bundle_adjust(scene, numCam, max_iter=10, rs=False, motion_prior=False, moti
     finally:
         if not return_handle:
             hd.close()
+            lap('close_ms')
 
     res = OptimizeResult(x=x, cost=st.cost, fun=r, jac=None, grad=None, optimality=st.optimality,
                          active_mask=np.zeros(fp.n, dtype=int), nfev=st.nfev, njev=st.njev,
