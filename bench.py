@@ -284,9 +284,11 @@ def main():
         dist.barrier()
     # two timed repetitions from the same start; the faster one is reported (host-side hiccups --
     # page cache, allocator -- have moved a single repetition by 0.4 s on a fresh box), both are listed
-    e2e_all = []
+    import gc
+    e2e_all, e2e_info = [], None
     for _rep in range(2):
         fp.unpack_into(fl, fp.x0)
+        gc.collect()                       # (the previous result's pinned arrays go back to the pool first)
         if world > 1:
             dist.barrier()
         pool0 = (_cabi.POOL.new_bytes, _cabi.POOL.reused_bytes)
@@ -297,10 +299,12 @@ def main():
         if world > 1:
             dist.all_reduce(dt_k, op=dist.ReduceOp.MAX)
         e2e_all.append(float(dt_k.item()))
-        if _rep == 0 or e2e_all[-1] <= min(e2e_all[:-1]):
-            res = res_k
+        if e2e_info is None or e2e_all[-1] <= min(e2e_all[:-1]):
+            e2e_info = {'nfev': int(res_k.nfev), 'host': res_k.stats.get('host'),
+                        'pinned_new': _cabi.POOL.new_bytes - pool0[0], 'pinned_reused': _cabi.POOL.reused_bytes - pool0[1]}
+        del res_k
     dt_e2e = min(e2e_all)
-    e2e_steps = max(res.nfev - 1, 1)
+    e2e_steps = max(e2e_info['nfev'] - 1, 1)
     e2e_val = N_total * e2e_steps / dt_e2e / 1e6
     h2d = (3 * fp.N * 8 + fp.n * 8) / e2e_steps
     d2h = (fp.n * 8 + (2 * fp.N + hd.M) * 8 + 2 * 3 * fp.N * 8) / e2e_steps
@@ -344,8 +348,8 @@ def main():
             'resid_jac_mdet_per_s': N_total / (ms[1] / 1e3) / 1e6,
             'roofline': roof, 'phases': phases, 'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'seconds': dt_e2e, 'seconds_all': e2e_all, 'steps': e2e_steps, 'host_phases_ms': res.stats.get('host'),
-                    'pinned_new_bytes': _cabi.POOL.new_bytes - pool0[0], 'pinned_reused_bytes': _cabi.POOL.reused_bytes - pool0[1]},
+                    'seconds': dt_e2e, 'seconds_all': e2e_all, 'steps': e2e_steps, 'host_phases_ms': e2e_info['host'],
+                    'pinned_new_bytes': e2e_info['pinned_new'], 'pinned_reused_bytes': e2e_info['pinned_reused']},
             'gpu_launches': int(st.launches), 'linear_solves': int(st.lm_iterations), 'final_cost': st.cost, 'cost0': st.cost0,
             'workload_gen_s': t_gen}
     if world == 1 and not a.no_cpu_baseline:
