@@ -96,6 +96,8 @@ class PinnedPool:
     reuse the same pages.  Falls back to pageable memory if pinning fails or the cap is hit."""
     CAP_BYTES = 24 << 30
 
+    MIN_BYTES = 16 << 20
+
     def __init__(self):
         self.free = []          # (nbytes, ptr)
         self.total = 0
@@ -105,6 +107,8 @@ class PinnedPool:
     def empty(self, n, dtype=np.float64):
         import weakref
         nbytes = max(int(n) * np.dtype(dtype).itemsize, 8)
+        if nbytes < self.MIN_BYTES:         # pinning costs milliseconds: only worth it for large transfers
+            return np.empty(int(n), dtype=dtype)
         lib = load()
         ptr = None
         for k, (sz, p) in enumerate(self.free):
