@@ -129,3 +129,70 @@ def test_dropin_installs_on_the_reference_module():
         common.Scene.BA = orig
         common.Scene.error_cam = common.Scene._reference_error_cam
         common.Scene.remove_outliers = common.Scene._reference_remove_outliers
+
+
+@pytest.mark.parametrize('name,scramble', [('gs_plain', False), ('rs_F_gap', False), ('rs_F_gap', True), ('calib_KE', True)])
+def test_k2_sliding_window_model_matches_dense(name, scramble):
+    """tests/proto/k2_window_proto.py (the bookkeeping ba_k2.cuh implements: control point j in slot
+    j & 3, flush of the slots that leave the window, D as upper triangle, ordering by control point)
+    == dense J^T J, J^T r of the reprojection rows.  `scramble` feeds the detections of each camera
+    in a random order, i.e. arbitrary span sequences (jumps, returns, uncovered gaps)."""
+    import helpers
+    from proto import k2_window_proto as k2
+    from mvus_b200.problem import FlatProblem
+    fl, truth, bakw = cases.make(name, det_per_cam=300)
+    fp = FlatProblem(fl, fl.numCam, **bakw)
+    r, span, J, mbase, mJ = helpers.emul_resjac(fp, fp.x0)
+    N, P, Pc, nc, C = fp.N, fp.P, fp.Pc, fp.nc, fp.C
+    J = np.asarray(J).reshape(2 * P, N)
+    Jg = helpers.expand_jacobian(fp, span, J).toarray()[:2 * N]
+    rr = np.asarray(r)[:2 * N]
+    H, g = Jg.T @ Jg, Jg.T @ rr
+    bw = 3
+    nb = (fp.n_ctrl + bw - 1) // bw
+    q = 3 * bw
+    out = None
+    rng = np.random.default_rng(5)
+    for i in range(nc):
+        a, b = int(fp.cam_ptr[i]), int(fp.cam_ptr[i + 1])
+        order = np.arange(a, b)
+        if scramble:                         # blocks of 1-7 detections in random order
+            cuts = np.cumsum(rng.integers(1, 8, size=b - a))
+            blocks = np.split(order, cuts[cuts < b - a])
+            order = np.concatenate([blocks[k] for k in rng.permutation(len(blocks))])
+        n_i = b - a
+        ru = rr[2 * a + (order - a)]
+        rv = rr[2 * a + n_i + (order - a)]
+        # the kernels store abs(residual) rows with the sign folded into J, so r and J are consistent as they are
+        out = k2.accumulate_camera(J[:P, order].T, J[P:, order].T, ru, rv, span[order], Pc, i, nc, bw, nb, out)
+    A, bc, D, E, W = out
+    cam_cols = lambda i: np.array([i, nc + i, 2 * nc + i] + list(range(3 * nc + i * C, 3 * nc + (i + 1) * C)))
+    ctrl_col = np.full(nb * q, -1)
+    for s in range(fp.S):
+        for l in range(int(fp.ncoef[s])):
+            for ax in range(3):
+                ctrl_col[3 * (int(fp.ctrl_off[s]) + l) + ax] = fp.n_other + 3 * fp.ctrl_off[s] + ax * fp.ncoef[s] + l
+    Hm, gm = np.zeros_like(H), np.zeros_like(g)
+    for i in range(nc):
+        cc = cam_cols(i)
+        Hm[np.ix_(cc, cc)] = A[i]
+        gm[cc] = -bc[i]
+    ok = ctrl_col >= 0
+    for i in range(nc):
+        cc = cam_cols(i)
+        Hm[np.ix_(ctrl_col[ok], cc)] = W[ok][:, i * Pc:(i + 1) * Pc]
+        Hm[np.ix_(cc, ctrl_col[ok])] = W[ok][:, i * Pc:(i + 1) * Pc].T
+    gm[ctrl_col[ok]] = -W[ok, -1]
+    for k in range(nb):
+        rows = ctrl_col[k * q:(k + 1) * q]
+        Dk = np.triu(D[k]) + np.triu(D[k], 1).T
+        assert np.abs(np.tril(D[k], -1)).max() == 0.0          # upper triangle only
+        rk = rows >= 0
+        Hm[np.ix_(rows[rk], rows[rk])] = Dk[np.ix_(rk, rk)]
+        if k + 1 < nb:
+            nxt = ctrl_col[(k + 1) * q:(k + 2) * q]
+            nk = nxt >= 0
+            Hm[np.ix_(rows[rk], nxt[nk])] = E[k][np.ix_(rk, nk)]
+            Hm[np.ix_(nxt[nk], rows[rk])] = E[k][np.ix_(rk, nk)].T
+    assert np.abs(Hm - H).max() <= 1e-11 * np.abs(H).max()
+    assert np.abs(gm - g).max() <= 1e-11 * np.abs(g).max()
