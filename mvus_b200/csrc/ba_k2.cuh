@@ -11,12 +11,15 @@
 // so consecutive runs (spans g, g+1, ...) share three of their four slots and only the slot
 // whose control point leaves the window is flushed (predicated FP64 REDs: camera x control ->
 // W~, the 8 lanes of equal fk writing 8 consecutive columns of one row; control x control -> E
-// or the UPPER triangle of D, damp_copy_kernel mirrors it) -- the L2 atomic units, not the SMs,
-// bound this kernel (measured: 11 of 22 ms at config 4 with one flush per run).  Camera-only
-// entries stay in registers for the whole tile, are summed over the CTA's warps through shared
-// memory and written once per tile.
+// or the UPPER triangle of D, damp_copy_kernel mirrors it).  Camera-only entries stay in
+// registers for the whole tile, are summed over the CTA's warps through shared memory and written
+// once per tile.  Tiles are visited in TIME order across cameras (tile_key_kernel + CUB sort) so
+// that the RED targets of concurrently running CTAs stay in L2: in camera-major order the DRAM
+// round trip of D, E and W~ cost 11 of 22 ms at config 4.  tests/proto/k2_window_proto.py is the
+// NumPy model of this bookkeeping (checked against the dense J^T J on the CPU).
 // Against the scalar version (one thread per entry, 4 shared loads per 2 FMAs, bound by
-// shared-memory bandwidth) a run of 5 detections costs 9 shared loads + 18 MMAs per warp.
+// shared-memory bandwidth: 29.6 ms) a run of 5 detections costs 9 shared loads + 18 MMAs per warp;
+// this version takes 15.4 ms and is bound by issue slots (flush bookkeeping), profiles/r1_notes.md.
 // HBM traffic per detection (algorithmic): read r (16 B) + span (4 B) + J (16 P B)
 //   -> 356 B (P=21) / 500 B (P=30); writes are O(runs), not O(detections).
 #pragma once
@@ -43,7 +46,7 @@ struct K2Cfg {
     static constexpr int THREADS = 2 * KT, WARPS = THREADS / 32;
     static constexpr int LDT = KT + 4;           // +4: conflict-free fragment loads (4 fm + fk pattern)
     static constexpr int CHUNK = KT / WARPS;     // detections per warp; runs are cut at chunk boundaries
-    static constexpr int CT = 8 * NCT;                 // run-table entries per run: position in the control tiles
+    static constexpr int CT = 8 * NCT;                 // positions in the control tiles
     // staged planes + span + run start + run span + per-run control-column table + misc
     static constexpr size_t SMEM = (size_t)(2 * (P + 1)) * LDT * sizeof(double) +
                                    (size_t)(KT + (KT + 1) + KT + 12 * KT + 16 + 8) * sizeof(int);
