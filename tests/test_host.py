@@ -196,3 +196,19 @@ def test_k2_sliding_window_model_matches_dense(name, scramble):
             Hm[np.ix_(nxt[nk], rows[rk])] = E[k][np.ix_(rk, nk)].T
     assert np.abs(Hm - H).max() <= 1e-11 * np.abs(H).max()
     assert np.abs(gm - g).max() <= 1e-11 * np.abs(g).max()
+
+
+def test_lm_driver_model_converges_like_the_shipped_solve():
+    """tests/proto/lm_proto.py (NumPy model of mvus_ba_solve's LM / trust-region control with a dense
+    solve): from the same start and with the same 10-evaluation cap it must not end above the shipped
+    SciPy call (oracle A), and the lambda search must stay cheap (linear solves per LM step)."""
+    from proto import lm_proto
+    from oracle import ba_oracle
+    for name in ('gs_plain', 'rs_KE_fpk30'):
+        fl, truth, bakw = cases.make(name, det_per_cam=150)
+        prob = ba_oracle.Problem(fl, fl.numCam, **bakw)
+        ra = prob.shipped_solve(prob.x0, max_nfev=10)
+        out = lm_proto.run(prob, prob.x0, max_nfev=10)
+        assert out['nfev'] <= 10
+        assert out['cost'] <= ra.cost * (1 + 1e-9), (name, out['cost'], ra.cost)
+        assert out['solves'] <= 2 * out['steps']
