@@ -875,8 +875,10 @@ inline void launch_syrk(mvus_ba_ctx* h, const double* Wrows, int64_t R, double* 
     if (R <= 0) return;
     const int ldw = h->ldw;
     const int nts = (ldw + SY_T - 1) / SY_T, npairs = nts * (nts + 1) / 2;
-    // ~4 waves of CTAs over the SMs, slabs a multiple of the K chunk
-    int64_t nslab = std::max<int64_t>(1, (4 * h->sm_count + npairs - 1) / npairs);
+    // ~8 waves of CTAs over the SMs (one 512-thread CTA of 128 registers per SM; CTA durations differ by
+    // up to 16:6 active warp tiles, so 4 waves left a tail of most of a CTA duration), slabs a multiple of
+    // the K chunk
+    int64_t nslab = std::max<int64_t>(1, (8 * h->sm_count + npairs - 1) / npairs);
     int slab = (int)std::max<int64_t>(256, ((R + nslab - 1) / nslab + SY_K - 1) / SY_K * SY_K);
     dim3 g(npairs, (unsigned)((R + slab - 1) / slab));
     syrk_kernel<<<g, 512, 0, h->st>>>(Wrows, R, ldw, slab, Sfull);
