@@ -164,6 +164,11 @@ class Handle:
         rc = self.lib.mvus_ba_create(ctypes.byref(desc), ctypes.byref(self.h))
         if rc != 0:
             raise MvusError('mvus_ba_create: %s' % self.lib.mvus_ba_last_error(None).decode())
+        self.reset_inputs(fp)
+
+    def reset_inputs(self, fp):
+        """(Re)load detections and splines of a FlatProblem with the same cameras / flags."""
+        self.fp = fp
         nc = fp.nc
         rows = [(ctypes.c_void_p * nc)(*[int(d[k].ctypes.data) for d in fp.dets]) for k in range(3)]
         self._check(self.lib.mvus_ba_set_detections_rows(self.h, _l(fp.N_cam), rows[0], rows[1], rows[2],

@@ -104,6 +104,8 @@ struct mvus_ba_ctx {
 
 namespace mvus {
 
+void invalidate_solver(mvus_ba_ctx* h);     // mvus_ba.cu
+
 inline int fail(mvus_ba_ctx* h, int code, const std::string& msg) {
     if (h) h->err = msg;
     return code;

@@ -4,11 +4,11 @@
 // one) so that the library itself loads on machines without NCCL and single-GPU use never
 // touches it.
 //
-// Round-1 scheme: detections are sharded across ranks (by camera / time chunk, the caller's
-// choice), every rank accumulates its partial A, bc, D, E, W~ and they are all-reduced over
-// NVLink; the (small, exact) solve then runs redundantly on every rank, so no further
-// exchange is needed inside an LM iteration.  Per LM iteration: 1 all-reduce of the normal
-// equations + 1 of the trial cost.
+// Detections are sharded across ranks (the caller's choice of shard; mvus_b200/shard.py cuts by
+// time), every rank accumulates its partial A, bc, D, E, W~; the camera blocks are all-reduced,
+// the spline-side arrays are reduced to the rank that owns the block range in the SHARDED exact
+// solve (ba_solve.cuh, solve_damped: local cyclic-reduction levels + a small top system), and
+// the trial costs are all-reduced so that every rank takes the same accept / reject decision.
 #pragma once
 #include <dlfcn.h>
 #include "ba_ctx.cuh"
@@ -146,6 +146,7 @@ extern "C" int mvus_ba_nccl_unique_id(char id_out[128]) {
 
 extern "C" int mvus_ba_comm_init(mvus_ba_handle h, int32_t world_size, int32_t rank, const char id[128]) {
     if (!h || !id || world_size < 1 || rank < 0 || rank >= world_size) return mvus::fail(h, MVUS_ERR_ARG, "bad argument");
+    if (world_size != h->world || rank != h->rank) mvus::invalidate_solver(h);   // block padding depends on the world size
     if (world_size == 1) { h->world = 1; h->rank = 0; return MVUS_OK; }
     std::string err;
     if (!mvus::nccl_api().load(err)) return mvus::fail(h, MVUS_ERR_NCCL, err);

@@ -94,6 +94,15 @@ extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
 }
 
 // ------------------------------------------------------------------------------------------
+// The solver arrays (bw, q, nb, Bc, ldw and every D/E/W~ buffer) are sized from n_ctrl, M and the
+// world size at the first solve.  Any later mvus_ba_set_detections / set_splines / comm_init must
+// make solver_alloc run again, or K2 and the cyclic-reduction levels would use stale block counts.
+void mvus::invalidate_solver(mvus_ba_ctx* h) {
+    h->A.release();
+    h->W.release();
+    h->J.release();
+}
+
 static int finish_dims(mvus_ba_ctx* h) {
     if (!(h->have_det && h->have_spl)) return MVUS_OK;
     h->n = h->n_other + 3 * h->n_ctrl;
@@ -162,6 +171,7 @@ static int set_detections_core(mvus_ba_ctx* h, const int64_t* count, const doubl
     }
     MV_CUDA(h, cudaStreamSynchronize(h->st));
     h->have_det = true;
+    invalidate_solver(h);
     return finish_dims(h);
 }
 
@@ -230,6 +240,7 @@ extern "C" int mvus_ba_set_splines(mvus_ba_handle h, int32_t S, const double* in
     }
     MV_CUDA(h, cudaStreamSynchronize(h->st));
     h->have_spl = true;
+    invalidate_solver(h);
     return finish_dims(h);
 }
 

@@ -33,3 +33,13 @@ def install(common_module, satellites=True):
             self, cams, thres=thres, verbose=verbose)
         Scene._reference_error_cam, Scene._reference_remove_outliers = orig_err, orig_rm
     return original
+
+
+def uninstall(common_module):
+    """Put the reference's own methods back."""
+    Scene = common_module.Scene
+    for name in ('BA', 'error_cam', 'remove_outliers'):
+        orig = Scene.__dict__.get('_reference_' + name)
+        if orig is not None:
+            setattr(Scene, name, orig)
+            delattr(Scene, '_reference_' + name)

@@ -46,6 +46,12 @@ class FlatProblem:
         self.cam_ptr = np.concatenate(([0], np.cumsum(self.N_cam))).astype(np.int64)
         self.N = int(self.cam_ptr[-1])
         cams = [scene.cameras[i] for i in self.seq]
+        for c in cams:
+            # the device carries (fx, fy, cx, cy) only, as Camera.vector2P does (common.py:1127-1144);
+            # a K with skew or a non-unit last row would silently project differently from P = K[R|t]
+            K = np.asarray(c.K, dtype=np.float64)
+            if abs(K[0, 1]) > 1e-12 * abs(K[0, 0]) or abs(K[1, 0]) > 0 or not np.array_equal(K[2], [0.0, 0.0, 1.0]):
+                raise ValueError('camera matrix with skew / non-unit last row is not supported on the device path')
         self.height = np.array([c.resolution[1] for c in cams], dtype=np.float64)
         self.calib = np.array([[c.K[0, 0], c.K[1, 1], c.K[0, 2], c.K[1, 2]] +
                                list(np.asarray(c.d, dtype=np.float64).reshape(5)) for c in cams],
@@ -64,6 +70,11 @@ class FlatProblem:
         self.n_other = self.nc * self.Pc
         self.n = self.n_other + 3 * self.n_ctrl
         self.x0 = self.pack(scene)
+        if self.rs_bounds:
+            rho = self.x0[2 * self.nc:3 * self.nc]
+            if (rho < 0.0).any() or (rho > 1.0).any():
+                # scipy: least_squares raises for an infeasible start (least_squares.py, "`x0` is infeasible.")
+                raise ValueError('`x0` is infeasible.')
 
     def _cat(self, row):
         return np.ascontiguousarray(np.concatenate([d[row] for d in self.dets])) if self.N else np.zeros(0)

@@ -11,10 +11,12 @@ the reference's ``error_BA`` closure, start vector and ``jac_BA`` pattern from i
                             (one of them moves detections across interval edges)
     pattern (rows, cols)    the reference's jac_sparsity
     shipped_cost/nfev       the reference's own Scene.BA(max_iter=10) result (SciPy 1.18.1)
-plus the flat scene description needed to rebuild the flight without the reference.
-It also runs the reference's main.py end to end on a dataset4-format synthetic flight
-(BASELINE config 1 shape, reduced) and stores the final Scene state as a fixture for the
-drop-in test.
+    book_*                  the pickled bookkeeping arrays (visible, global_traj,
+                            global_detections, frame_id_all, global_time_stamps_all, traj) as the
+                            reference leaves them after error_BA(x0) (ref_shim.reference_bookkeeping)
+The flights themselves are rebuilt from their seeds (tests/cases.py), so nothing else is stored.
+(main.py end to end is not a fixture: it runs live against oracle/_ref in
+tests/test_gpu_reference.py::test_main_py_through_the_dropin.)
 """
 import io
 import os
@@ -59,8 +61,10 @@ def main():
         ref2 = ref_shim.to_reference_scene(fl)
         with contextlib.redirect_stdout(io.StringIO()):
             res = ref2.BA(fl.numCam, **bakw)
+        book = ref_shim.reference_bookkeeping(fl, fl.numCam, x=x0, **bakw)
+        book = {'book_' + k: v for k, v in book.items()}
         out = os.path.join(HERE, 'ba_%s.npz' % name)
-        np.savez_compressed(out, x0=x0, xs=np.array(xs), rs=np.array(rs),
+        np.savez_compressed(out, **book, x0=x0, xs=np.array(xs), rs=np.array(rs),
                             pat_rows=rows.astype(np.int32), pat_cols=rows.astype(np.int32) * 0 + cols.astype(np.int32),
                             pat_shape=np.array(np.asarray(A).shape), shipped_cost=res.cost,
                             shipped_nfev=res.nfev, shipped_x=res.x,

@@ -121,3 +121,41 @@ def numpy_all_detect_to_traj(scene, cams):
     keep = np.isin(tmp[2], traj[0])
     tmp = np.vstack((tmp[:, keep], traj[1:]))
     return np.vstack((np.arange(tmp.shape[1]), tmp))
+
+
+def check_normal_equations(fp, prob, x, A, g, Hss, Hcs, cost, rtol=1e-9, n_sample=3000):
+    """Compare K2's output (mvus_ba_normal_equations layout) with J^T J / J^T r formed from the
+    ORACLE's Jacobian, sparse all the way so that it works at the BASELINE sizes: camera blocks, the
+    whole gradient, the camera x control-point coupling and sampled control-point band blocks."""
+    ro = prob.residual(x)
+    Jo = (prob.jacobian(x).tocsc() @ sp.diags(prob.free_mask().astype(float))).tocsc()
+    assert abs(cost - 0.5 * ro @ ro) <= 1e-12 * cost
+    go = Jo.T @ ro
+    assert np.abs(g - go).max() <= rtol * np.abs(go).max()
+    nc, C = fp.nc, fp.C
+    cam_cols = [np.array([i, nc + i, 2 * nc + i] + list(range(3 * nc + i * C, 3 * nc + (i + 1) * C)))
+                for i in range(nc)]
+    for i in range(nc):
+        Jc = Jo[:, cam_cols[i]]
+        blk = (Jc.T @ Jc).toarray()
+        assert np.abs(A[i] - blk).max() <= rtol * max(np.abs(blk).max(), 1e-300), i
+    # control-point columns in control-point-major order (the solver's numbering)
+    cols = np.concatenate([(fp.n_other + 3 * fp.ctrl_off[s] + np.arange(3)[None, :] * fp.ncoef[s]
+                            + np.arange(fp.ncoef[s])[:, None]).ravel() for s in range(fp.S)])
+    Js = Jo[:, cols]
+    Hc = (Jo[:, np.concatenate(cam_cols)].T @ Js).toarray()
+    assert Hcs.shape == Hc.shape
+    assert np.abs(Hcs - Hc).max() <= rtol * np.abs(Hc).max()
+    band = Hss.shape[1]
+    rng = np.random.default_rng(1)
+    pick = np.unique(np.concatenate(([0, 1, 2, fp.n_ctrl - 1, fp.n_ctrl - 2],
+                                     rng.integers(0, fp.n_ctrl, n_sample))))
+    scale = abs(Js).max() ** 2
+    for i in pick:
+        hi = min(fp.n_ctrl, i + band)
+        blk = (Js[:, 3 * i:3 * i + 3].T @ Js[:, 3 * i:3 * hi]).toarray()        # 3 x 3 (hi - i)
+        mine = np.concatenate([Hss[i, dj] for dj in range(hi - i)], axis=1)
+        assert np.abs(mine - blk).max() <= rtol * max(np.abs(blk).max(), 1e-6 * scale), int(i)
+    # nothing outside the band: the rows further than `band` control points apart are orthogonal
+    far = Js[:, :3].T @ Js[:, 3 * band:] if fp.n_ctrl > band else None
+    assert far is None or abs(far).max() == 0.0

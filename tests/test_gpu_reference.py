@@ -1,0 +1,235 @@
+"""GPU tests against the UNMODIFIED reference running next to the CUDA path on the same box
+(oracle/_ref, made by oracle/make_ref.py) and against the golden fixtures the reference produced
+(tests/golden/*.npz), plus the reference edge cases round 1 only covered on the host emulation:
+degree-1 splines, undist_points=False, opt_sync=False, the v row of detections_global."""
+import io
+import contextlib
+import os
+import pickle
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import cases
+import helpers
+from mvus_b200 import _cabi, dropin, synth
+from mvus_b200.problem import FlatProblem
+from oracle import ba_oracle, ref_shim
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+needs_ref = pytest.mark.skipif(not ref_shim.available(), reason='oracle/_ref not present (run oracle/make_ref.py)')
+
+
+def _parity(fl, bakw, solve=True):
+    fp = FlatProblem(fl, fl.numCam, **bakw)
+    prob = ba_oracle.Problem(fl, fl.numCam, **bakw)
+    hd = _cabi.Handle(fp, max_nfev=8)
+    free = sp.diags(prob.free_mask().astype(float))
+    rng = np.random.default_rng(11)
+    for x in (prob.x0, prob.x0 + rng.normal(size=prob.n) * 1e-4 * np.maximum(1.0, np.abs(prob.x0))):
+        r, span, J, mbase, mJ = hd.residual_jacobian(x)
+        ro = prob.residual(x)
+        assert np.abs(r - ro).max() <= RTOL * max(1.0, np.abs(ro).max())
+        Jg = helpers.expand_jacobian(fp, span, J, mbase, mJ)
+        Jo = (prob.jacobian(x).tocsc() @ free).tocsc()
+        colmax = np.maximum(abs(Jo).max(axis=0).toarray().ravel(), 1e-300)
+        assert (abs(Jg - Jo).tocsc().max(axis=0).toarray().ravel() / colmax).max() <= RTOL
+    A, g, Hss, Hcs, cost = hd.normal_equations(prob.x0)
+    helpers.check_normal_equations(fp, prob, prob.x0, A, g, Hss, Hcs, cost, RTOL, n_sample=200)
+    if solve:
+        x, rr, st = hd.solve(fp.x0)
+        assert st.cost < st.cost0 and abs(prob.cost(x) - st.cost) <= 1e-9 * st.cost
+    hd.close()
+    return fp, prob
+
+
+def _linear_spline_flight(name='rs_F_gap'):
+    """traj_to_spline falls back to k = 1 when the cubic fit throws (common.py:266-267)."""
+    fl, truth, bakw = cases.make(name)
+    t = fl.spline['tck'][0]
+    kn = np.linspace(t[0][0], t[0][-1], 14)
+    knots = np.concatenate(([kn[0]], kn, [kn[-1]]))
+    c = synth.gt_trajectory(kn) + np.random.default_rng(0).normal(size=(3, len(kn))) * 0.01
+    fl.spline['tck'][0] = [knots, [c[0].copy(), c[1].copy(), c[2].copy()], 1]
+    return fl, bakw
+
+
+def test_degree_one_spline_on_device(built_lib):
+    fl, bakw = _linear_spline_flight()
+    assert [int(t[2]) for t in fl.spline['tck']] == [1, 3]
+    _parity(fl, bakw)
+    # spline_to_traj on a linear spline against FITPACK
+    from scipy.interpolate import splev
+    interval = np.asarray(fl.spline['int'])
+    got = fl.spline_to_traj()
+    ts = np.arange(interval[0, 0], interval[1, -1], 1.0)
+    tp = ts[(ts >= interval[0, 0]) & (ts <= interval[1, 0])]
+    want = np.asarray(splev(tp, fl.spline['tck'][0]))
+    assert np.abs(got[1:, :len(tp)] - want).max() <= 1e-10 * np.abs(want).max()
+
+
+@pytest.mark.parametrize('name', ['rs_F_gap', 'calib_KE'])
+def test_undist_points_false_on_device(name, built_lib):
+    """settings['undist_points'] = False: the raw pixel is the observation (common.py:126)."""
+    fl, truth, bakw = cases.make(name)
+    fl.settings['undist_points'] = False
+    fp, prob = _parity(fl, bakw)
+    assert not fp.undist
+    hd = _cabi.Handle(fp)
+    dg = hd.detections_global(fp.x0)
+    hd.close()
+    for k in range(fp.nc):
+        assert np.array_equal(dg[k][1:], fl.detections[k][1:])
+
+
+@pytest.mark.parametrize('name', ['gs_plain', 'calib_KE'])
+def test_opt_sync_false_on_device(name, built_lib):
+    """settings['opt_sync'] = False freezes alpha and beta (common.py:512-515): their Jacobian
+    columns are zero and a solve leaves them untouched."""
+    fl, truth, bakw = cases.make(name)
+    fl.settings['opt_sync'] = False
+    a0, b0 = fl.alpha.copy(), fl.beta.copy()
+    fp, prob = _parity(fl, bakw, solve=False)
+    assert not fp.opt_sync and not prob.free_mask()[:2 * fp.nc].any()
+    res = fl.BA(fl.numCam, max_iter=8, **bakw)
+    assert res.cost < res.stats['cost0']
+    assert np.array_equal(fl.alpha, a0) and np.array_equal(fl.beta, b0)
+
+
+@pytest.mark.parametrize('name', ['rs_F_gap', 'calib_KE'])
+def test_detections_global_all_rows(name, built_lib):
+    """detections_global = [t; u_obs; v_obs] (common.py:105-127): all three rows against the
+    oracle, and against the reference's own detection_to_global when it is on the box."""
+    fl, truth, bakw = cases.make(name)
+    fp = FlatProblem(fl, fl.numCam, **bakw)
+    prob = ba_oracle.Problem(fl, fl.numCam, **bakw)
+    hd = _cabi.Handle(fp)
+    dg = hd.detections_global(fp.x0)
+    hd.close()
+    ref = ref_shim.to_reference_scene(fl) if ref_shim.available() else None
+    for i in range(fl.numCam):
+        c = prob._cam_terms(prob.x0, i)
+        for row, key in enumerate(('t', 'uo', 'vo')):
+            assert np.abs(dg[i][row] - c[key]).max() <= RTOL * max(1.0, np.abs(c[key]).max()), (i, key)
+        if ref is not None:
+            assert np.abs(dg[i] - ref.detections_global[i]).max() <= RTOL * np.abs(ref.detections_global[i]).max()
+
+
+# ---------------------------------------------------------------------------------------------
+# a12: the pickled bookkeeping arrays, pinned to the reference
+def _device_bookkeeping(name):
+    fl, truth, bakw = cases.make(name)
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = fl.BA(fl.numCam, max_iter=1, **bakw)          # one evaluation: the Scene stays at x0
+    assert res.nfev == 1
+    return fl, bakw, res
+
+
+def _check_bookkeeping(fl, want):
+    for i in range(fl.numCam):
+        assert np.array_equal(np.asarray(fl.visible[i]), want['visible_%d' % i])
+    assert fl.global_traj.shape == want['global_traj'].shape
+    assert np.array_equal(fl.global_traj[:3], want['global_traj'][:3])          # index, camera, frame
+    assert np.abs(fl.global_traj[3:] - want['global_traj'][3:]).max() <= RTOL * np.abs(want['global_traj'][3:]).max()
+    assert fl.global_detections.shape == want['global_detections'].shape
+    assert np.array_equal(fl.global_detections[:2], want['global_detections'][:2])
+    assert np.abs(fl.global_detections[2] - want['global_detections'][2]).max() <= RTOL * np.abs(want['global_detections'][2]).max()
+    assert np.array_equal(fl.frame_id_all, want['frame_id_all'])
+    assert np.abs(fl.global_time_stamps_all - want['global_time_stamps_all']).max() <= RTOL * np.abs(want['global_time_stamps_all']).max()
+    assert fl.traj.shape == want['traj'].shape
+    assert np.array_equal(fl.traj[0], want['traj'][0])
+    assert np.abs(fl.traj[1:] - want['traj'][1:]).max() <= RTOL * np.abs(want['traj'][1:]).max()
+
+
+@pytest.mark.parametrize('name', ['rs_F_gap', 'calib_KE'])
+def test_bookkeeping_matches_golden(name, built_lib):
+    """visible / global_traj / global_detections / frame_id_all / global_time_stamps_all / traj
+    as the REFERENCE leaves them after error_BA(x0) (tests/golden/make_golden.py stores them)."""
+    z = np.load(os.path.join(GOLD, 'ba_%s.npz' % name))
+    if 'book_global_traj' not in z.files:
+        pytest.skip('golden fixture without bookkeeping arrays')
+    fl, bakw, res = _device_bookkeeping(name)
+    want = {k[5:]: z[k] for k in z.files if k.startswith('book_')}
+    _check_bookkeeping(fl, want)
+
+
+@needs_ref
+@pytest.mark.parametrize('name', ['rs_F_gap', 'rs_KE_fpk30'])
+def test_bookkeeping_matches_live_reference(name, built_lib):
+    fl, bakw, res = _device_bookkeeping(name)
+    fl0, _, _ = cases.make(name)
+    want = ref_shim.reference_bookkeeping(fl0, fl0.numCam, **bakw)
+    _check_bookkeeping(fl, want)
+
+
+# ---------------------------------------------------------------------------------------------
+# config 1: the reference's own main.py, end to end, with and without the drop-in
+@needs_ref
+def test_main_py_through_the_dropin(built_lib, tmp_path):
+    """BASELINE config 1 (4 cameras, global shutter, cf_exact, no motion prior; reduced to 1500
+    detections per camera so that the untouched reference finishes in ~15 s): main.py:18-97 runs
+    unmodified twice on the same dataset4-format files -- once as shipped (SciPy BA on the CPU),
+    once with mvus_b200.dropin.install (every BA / error_cam / remove_outliers on the B200)."""
+    cfg_ref = synth.write_dataset(str(tmp_path / 'ref'), nc=4, det_per_cam=1500, seed=0)
+    cfg_gpu = synth.write_dataset(str(tmp_path / 'gpu'), nc=4, det_per_cam=1500, seed=0)
+    f_ref, log_ref = ref_shim.run_main(cfg_ref)
+    f_gpu, log_gpu = ref_shim.run_main(cfg_gpu, install=dropin.install, uninstall=dropin.uninstall)
+    assert 'Finished!' in log_ref and 'Finished!' in log_gpu
+    assert log_gpu.count('Doing BA with') == log_ref.count('Doing BA with') == 6      # 2 per step, 3 steps
+    common = ref_shim.load()
+    assert 'BA' in common.Scene.__dict__ and not hasattr(common.Scene, '_reference_BA')   # uninstalled
+    # per-camera mean reprojection error of the final scene, evaluated by the REFERENCE's error_cam
+    e_ref = np.array([np.mean(f_ref.error_cam(i)) for i in f_ref.sequence])
+    e_gpu = np.array([np.mean(f_gpu.error_cam(i)) for i in f_gpu.sequence])
+    assert f_gpu.sequence == f_ref.sequence
+    assert (e_gpu <= 1.05 * e_ref + 1e-3).all(), (e_gpu, e_ref)
+    assert e_gpu.max() < 1.0                                # 0.5 px noise
+    # output contract (main.py:85-94, README.md:205-294): same fields, picklable, loadable
+    with open(f_gpu.settings['path_output'], 'rb') as fh:
+        back = pickle.load(fh)
+    for k in ('numCam', 'cameras', 'detections', 'detections_global', 'alpha', 'beta', 'rs', 'spline',
+              'traj', 'sequence', 'visible', 'settings', 'out'):
+        assert hasattr(back, k), k
+    assert type(back).__module__ == 'reconstruction.common'
+    assert back.traj.shape[0] == 4 and back.traj.shape[1] > 100
+    assert len(back.detections_global) == 4 and all(d.shape[0] == 3 for d in back.detections_global)
+    for c in back.cameras:
+        assert np.allclose(c.P, c.K @ np.hstack((c.R, c.t.reshape(3, 1))), atol=1e-9)
+    # the two reconstructions describe the same flight: trajectories agree after a similarity fit
+    ia, ib = np.asarray(f_ref.spline['int']), np.asarray(f_gpu.spline['int'])
+    tt = np.linspace(max(ia[0, 0], ib[0, 0]), min(ia[1, -1], ib[1, -1]), 2000)
+    tr_ref, tr_gpu = f_ref.spline_to_traj(t=tt).copy(), f_gpu.spline_to_traj(t=tt).copy()
+    t_common = np.intersect1d(tr_ref[0], tr_gpu[0])
+    assert len(t_common) > 1500
+    P = tr_gpu[1:, np.isin(tr_gpu[0], t_common)]
+    Q = tr_ref[1:, np.isin(tr_ref[0], t_common)]
+    mp, mq = P.mean(1, keepdims=True), Q.mean(1, keepdims=True)
+    U, S, Vt = np.linalg.svd((Q - mq) @ (P - mp).T)
+    D = np.diag([1, 1, np.sign(np.linalg.det(U @ Vt))])
+    s = np.trace(np.diag(S) @ D) / np.sum((P - mp) ** 2)
+    err = np.sqrt(np.sum((s * (U @ D @ Vt) @ (P - mp) + mq - Q) ** 2, axis=0))
+    scale = np.sqrt(np.mean(np.sum((Q - mq) ** 2, axis=0)))
+    assert np.sqrt(np.mean(err ** 2)) < 0.02 * scale
+
+
+def test_setters_after_a_solve_resize_the_solver(built_lib):
+    """The C ABI allows mvus_ba_set_splines / set_detections again on a handle that has already
+    solved (include/mvus_ba.h): the solver's block counts must follow."""
+    fl, truth, bakw = cases.make('rs_F_gap')
+    fp = FlatProblem(fl, fl.numCam, **bakw)
+    hd = _cabi.Handle(fp, max_nfev=6)
+    hd.solve(fp.x0)
+    fl2, _, _ = cases.make('rs_F_gap', frames_per_knot=6.0, det_per_cam=700)     # more knots, more detections
+    fp2 = FlatProblem(fl2, fl2.numCam, **bakw)
+    hd.reset_inputs(fp2)
+    x, r, st = hd.solve(fp2.x0)
+    fresh = _cabi.Handle(fp2, max_nfev=6)
+    x2, r2, st2 = fresh.solve(fp2.x0)
+    fresh.close()
+    hd.close()
+    assert st.nfev == st2.nfev and abs(st.cost - st2.cost) <= 1e-9 * st2.cost
+    prob = ba_oracle.Problem(fl2, fl2.numCam, **bakw)
+    assert abs(prob.cost(x) - st.cost) <= 1e-9 * st.cost

@@ -1,0 +1,110 @@
+"""GPU parity AT THE BASELINE.json SIZES (run with -m gpu on the B200): the CUDA path, through the
+C ABI, against (a) the oracle (oracle/ba_oracle.py, vectorised NumPy -- it finishes in seconds at
+these sizes) on ALL rows and (b) the UNMODIFIED reference's own error function (oracle/_ref, made by
+oracle/make_ref.py; reference methods Scene.error_cam / error_motion / all_detect_to_traj driven as
+common.py:448-487 does) when it travelled to the box.
+
+  config 2: 7 cameras x 100 000 detections, rolling shutter, motion F (w = 1e4), 15 frames/knot
+  config 3: the same with opt_calib (15 camera unknowns) and motion KE
+  config 4: 1 000 000 detections per camera on a 200 000-coefficient spline (5 frames/knot); two whole
+            cameras of the 64 (the 2e5-span lookup table, int32 span packing and time-ordered tile
+            sort are the config-4 code paths; 64 cameras only repeat them)
+Tolerances: residual and Jacobian 1e-9 relative (BASELINE.json), normal equations 1e-9.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import helpers
+from mvus_b200 import _cabi, synth
+from mvus_b200.problem import FlatProblem
+from oracle import ba_oracle, ref_shim
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def _flight(cfg):
+    if cfg == 'cfg2':
+        kw = dict(nc=7, det_per_cam=100000, frames_per_knot=15.0, rolling_shutter=True, distortion=True,
+                  motion_type='F', motion_weights=1e4, uncovered=0.01)
+        bakw = dict(rs=True, motion_reg=True, motion_weights=1e4)
+    elif cfg == 'cfg3':
+        kw = dict(nc=7, det_per_cam=100000, frames_per_knot=15.0, rolling_shutter=True, distortion=True,
+                  opt_calib=True, motion_type='KE', motion_weights=1e2, uncovered=0.01)
+        bakw = dict(rs=True, motion_reg=True, motion_weights=1e2)
+    else:
+        kw = dict(nc=2, det_per_cam=1000000, n_coef=200000, rolling_shutter=True, distortion=True,
+                  motion_type='F', motion_weights=1e4, uncovered=0.0)
+        bakw = dict(rs=True, motion_reg=True, motion_weights=1e4)
+    fl, truth = synth.make_flight(**kw)
+    return fl, bakw
+
+
+def _points(prob):
+    rng = np.random.default_rng(5)
+    x0 = prob.x0
+    yield x0
+    yield x0 + rng.normal(size=x0.shape) * 1e-4 * np.maximum(1.0, np.abs(x0))
+    x = x0.copy()
+    x[prob.nc:2 * prob.nc] += 0.5          # detections cross interval edges and knot spans
+    yield x
+
+
+@pytest.mark.parametrize('cfg', ['cfg2', 'cfg3', 'cfg4_two_cameras'])
+def test_full_size_residual_jacobian_parity(cfg, built_lib):
+    fl, bakw = _flight(cfg)
+    fp = FlatProblem(fl, fl.numCam, **bakw)
+    prob = ba_oracle.Problem(fl, fl.numCam, **bakw)
+    assert fp.N >= 650000
+    hd = _cabi.Handle(fp)
+    free = sp.diags(prob.free_mask().astype(float))
+    ref = ref_shim.to_reference_scene(fl) if ref_shim.available() else None
+    for k, x in enumerate(_points(prob)):
+        ro = prob.residual(x)
+        r = hd.residual(x)
+        assert r.shape == ro.shape
+        assert np.abs(r - ro).max() <= RTOL * max(1.0, np.abs(ro).max()), (cfg, k)
+        if ref is not None:                       # the reference's own error function, all rows
+            rr = ref_shim.reference_error_BA(ref, fl.numCam, x, motion_reg=bakw.get('motion_reg', False),
+                                             motion_weights=bakw.get('motion_weights', 1))
+            assert rr.shape == r.shape
+            assert np.abs(r - rr).max() <= RTOL * max(1.0, np.abs(rr).max()), (cfg, k, 'reference')
+        if k == 2 and cfg != 'cfg2':
+            continue                              # Jacobian at two points per configuration (time)
+        r2, span, J, mbase, mJ = hd.residual_jacobian(x)
+        assert np.array_equal(r2, r)
+        Jg = helpers.expand_jacobian(fp, span, J, mbase, mJ)
+        Jo = (prob.jacobian(x).tocsc() @ free).tocsc()
+        colmax = np.maximum(abs(Jo).max(axis=0).toarray().ravel(), 1e-300)
+        err = abs(Jg - Jo).tocsc().max(axis=0).toarray().ravel() / colmax
+        assert err.max() <= RTOL, (cfg, k, int(err.argmax()), float(err.max()))
+    hd.close()
+
+
+@pytest.mark.parametrize('cfg', ['cfg2', 'cfg4_two_cameras'])
+def test_full_size_normal_equations_parity(cfg, built_lib):
+    """K2 at full size: camera blocks, the whole gradient, the camera x control-point coupling and
+    (sampled) control-point band blocks against J^T J / J^T r formed from the ORACLE's Jacobian."""
+    fl, bakw = _flight(cfg)
+    fp = FlatProblem(fl, fl.numCam, **bakw)
+    prob = ba_oracle.Problem(fl, fl.numCam, **bakw)
+    hd = _cabi.Handle(fp)
+    x = prob.x0
+    A, g, Hss, Hcs, cost = hd.normal_equations(x)
+    hd.close()
+    helpers.check_normal_equations(fp, prob, x, A, g, Hss, Hcs, cost, RTOL)
+
+
+def test_full_size_solve_against_oracle_cost(built_lib):
+    """Config 2 full size: the cost the device reports at x* is the ORACLE's cost at x*, and one
+    more oracle-side check of optimality: the oracle gradient at x* is far below the start's."""
+    fl, bakw = _flight('cfg2')
+    fp = FlatProblem(fl, fl.numCam, **bakw)
+    prob = ba_oracle.Problem(fl, fl.numCam, **bakw)
+    hd = _cabi.Handle(fp, max_nfev=15)
+    x, r, st = hd.solve(fp.x0)
+    hd.close()
+    assert abs(prob.cost(x) - st.cost) <= 1e-9 * st.cost
+    assert np.abs(prob.residual(x) - r).max() <= RTOL * np.abs(r).max()
+    assert st.cost < 0.2 * prob.cost(prob.x0)
