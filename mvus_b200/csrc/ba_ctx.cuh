@@ -14,6 +14,19 @@ namespace mvus {
 
 constexpr int TILE_DET = 128;      // detections per CTA tile (one camera per tile)
 
+// Compact block-row Jacobian in HBM: one BLOCK per 32 detections (= one warp of a K1 tile, 4 per tile):
+//   [2P+2 planes x 32 doubles | 32 span ints]; planes: u columns (P), v columns (P), r_u, r_v.
+// Element (plane p, detection t) sits at jblk_off(p, t): the XOR permutes the 32-byte sectors of a
+// 256-byte plane row (stores stay coalesced) so that K2's MMA fragment loads are bank-conflict free.
+template <int P>
+struct JBlk {
+    static constexpr int NPL = 2 * P + 2;
+    static constexpr int BLK_D = NPL * 32 + 16;       // doubles per block
+    static constexpr int SPAN_OFF = NPL * 32;         // (in doubles) start of the 32 span ints
+};
+__host__ __device__ __forceinline__ int jblk_off(int plane, int t) { return plane * 32 + (t ^ ((plane & 3) << 2)); }
+inline int jblk_doubles(int P) { return (2 * P + 2) * 32 + 16; }
+
 // Device buffer on the stream-ordered allocator.  The device's default memory pool is told to
 // keep freed memory (release threshold = max, set in mvus_ba_create), so the ~35 GB a config-4
 // handle needs are cudaMalloc'ed once per process and re-used by every later BA call (the
@@ -81,7 +94,9 @@ struct mvus_ba_ctx {
     // per-evaluation state
     mvus::DevBuf<double> x, x_trial, camprep, r, J, mJ, partial, scratch, gt_out;
     mvus::DevBuf<int> span, mbase, flag, frozen;
-    mvus::DevBuf<int> tile_key, tile_key2, tile_id, tile_perm;   // K2 tile order (by first span index)
+    // K2 work list: chunks of up to 4 consecutive tiles of one camera, visited in time order
+    int n_chunks = 0;
+    mvus::DevBuf<int> chunk_tile0, chunk_nt, chunk_key, chunk_key2, chunk_id, chunk_perm, k2_queue;
     mvus::DevBuf<unsigned char> sort_tmp;
     double* h_pin = nullptr;      // pinned scratch for scalars
     size_t h_pin_n = 0;
@@ -91,9 +106,12 @@ struct mvus_ba_ctx {
     int64_t nb = 0;               // super-blocks
     int ncP = 0, ldw = 0;         // camera unknowns, leading dimension of W~ (ncP + 1 rhs column)
     mvus::DevBuf<double> A, D, E, W, Dw, Ew, Ww, ZL, Sd, dlt_c, dlt_s, diag_c, diag_s, gvec, xs;
+    mvus::DevBuf<double> Hb;             // K2's control x control band array (ba_k2.cuh, band_to_blocks_kernel)
     mvus::DevBuf<double> bs;             // spline right-hand side (-J^T r) as a contiguous vector
     mvus::DevBuf<double> Dt, ZLt, dst;   // top-level system of the sharded solve
     int64_t Bc = 1;                      // chunk size (super-blocks) of the sharded solve
+    size_t w_guard = 0;                  // doubles in front of W~ inside the allocation W (K2's guard rows)
+    double* Wp() const { return W.p ? W.p + w_guard : nullptr; }
     int launches = 0;
     int64_t cost_slot = 0;        // index in `partial` where the last evaluation left sum r^2
 

@@ -45,13 +45,13 @@ __global__ void observe_kernel(const int* __restrict__ tile_cam, const int64_t* 
     }
 }
 
-struct PlaneSink {
-    double* J;
-    int64_t N, d;
-    int P;
+// Jacobian block of the warp (ba_ctx.cuh, JBlk): column p of the u row -> plane p, of the v row -> plane P + p
+struct BlockSink {
+    double* blk;
+    int lt, P;
     __device__ __forceinline__ void put(int p, double a, double b) {
-        __stcs(J + (int64_t)p * N + d, a);
-        __stcs(J + (int64_t)(P + p) * N + d, b);
+        __stcs(blk + jblk_off(p, lt), a);
+        __stcs(blk + jblk_off(P + p, lt), b);
     }
 };
 struct NullSink {
@@ -78,8 +78,7 @@ resjac_kernel(SplineView sp, const double* __restrict__ x, const double* __restr
               const double* __restrict__ frame, const double* __restrict__ xr,
               const double* __restrict__ yr, const double* __restrict__ obs_u,
               const double* __restrict__ obs_v, int undist, int opt_sync, int opt_rs, int64_t N,
-              double* __restrict__ r, int* __restrict__ span, double* __restrict__ J,
-              double* __restrict__ partial) {
+              double* __restrict__ r, double* __restrict__ Jb, double* __restrict__ partial) {
     __shared__ double s_cam[CAMPREP_DOUBLES];
     __shared__ double s_red[TILE_DET / 32];
     const int tl = blockIdx.x;
@@ -100,9 +99,14 @@ resjac_kernel(SplineView sp, const double* __restrict__ x, const double* __restr
         int sp_out;
         FreeMask fm{opt_sync != 0, opt_rs != 0};
         if (WANTJ) {
-            PlaneSink sink{J, N, d, 3 + (CALIB ? 15 : 6) + 12};
+            constexpr int P = 3 + (CALIB ? 15 : 6) + 12;
+            const int lt = threadIdx.x & 31;
+            double* blk = Jb + ((size_t)tl * (TILE_DET / 32) + (threadIdx.x >> 5)) * JBlk<P>::BLK_D;
+            BlockSink sink{blk, lt, P};
             resjac_one<CALIB, true>(c, undist != 0, fm, f, xx, yy, ou, ov, sp, x, ru, rv, sp_out, sink);
-            span[d] = sp_out;
+            __stcs(blk + jblk_off(2 * P, lt), ru);
+            __stcs(blk + jblk_off(2 * P + 1, lt), rv);
+            reinterpret_cast<int*>(blk + JBlk<P>::SPAN_OFF)[lt] = sp_out;
         } else {
             NullSink sink;
             resjac_one<CALIB, false>(c, undist != 0, fm, f, xx, yy, ou, ov, sp, x, ru, rv, sp_out, sink);
@@ -159,6 +163,19 @@ __global__ void reduce_partial_kernel(const double* __restrict__ partial, int64_
         __syncthreads();
     }
     if (threadIdx.x == 0) out[0] = sh[0];
+}
+
+// Diagnostic getter (mvus_ba_residual_jacobian): Jacobian blocks -> column planes J[2P][N] and span[N].
+__global__ void deblock_kernel(const double* __restrict__ Jb, int P, const int64_t* __restrict__ tile_start,
+                               const int* __restrict__ tile_cnt, int64_t N, double* __restrict__ J,
+                               int* __restrict__ span) {
+    const int tl = blockIdx.x, t = threadIdx.x;
+    if (t >= tile_cnt[tl]) return;
+    const int blk_d = (2 * P + 2) * 32 + 16;
+    const double* blk = Jb + ((size_t)tl * (TILE_DET / 32) + (t >> 5)) * blk_d;
+    const int64_t d = tile_start[tl] + t;
+    for (int p = 0; p < 2 * P; ++p) J[(int64_t)p * N + d] = blk[jblk_off(p, t & 31)];
+    span[d] = reinterpret_cast<const int*>(blk + (2 * P + 2) * 32)[t & 31];
 }
 
 // detections_global (common.py:105-127): time stamp and observation per detection.

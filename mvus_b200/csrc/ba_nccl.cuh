@@ -91,7 +91,7 @@ inline int reduce_normal_equations(mvus_ba_ctx* h, bool full) {
     if (full || !api.Reduce || !api.GroupStart || !api.GroupEnd) {
         rc = nccl_sum(h, h->D.p, h->nb * qq);
         if (!rc) rc = nccl_sum(h, h->E.p, h->nb * qq);
-        if (!rc) rc = nccl_sum(h, h->W.p, (size_t)h->nb * wn);
+        if (!rc) rc = nccl_sum(h, h->Wp(), (size_t)h->nb * wn);
         return rc;
     }
     int e = api.GroupStart();
@@ -102,7 +102,7 @@ inline int reduce_normal_equations(mvus_ba_ctx* h, bool full) {
         const size_t nblk = (size_t)(hi - lo);
         e = api.Reduce(h->D.p + lo * qq, h->D.p + lo * qq, nblk * qq, NCCL_FLOAT64, NCCL_SUM, r, h->nccl_comm, h->st);
         if (!e) e = api.Reduce(h->E.p + lo * qq, h->E.p + lo * qq, nblk * qq, NCCL_FLOAT64, NCCL_SUM, r, h->nccl_comm, h->st);
-        if (!e) e = api.Reduce(h->W.p + lo * wn, h->W.p + lo * wn, nblk * wn, NCCL_FLOAT64, NCCL_SUM, r, h->nccl_comm, h->st);
+        if (!e) e = api.Reduce(h->Wp() + lo * wn, h->Wp() + lo * wn, nblk * wn, NCCL_FLOAT64, NCCL_SUM, r, h->nccl_comm, h->st);
     }
     const int e2 = api.GroupEnd();
     if (e || e2) return fail(h, MVUS_ERR_NCCL, "grouped ncclReduce of the normal equations failed");

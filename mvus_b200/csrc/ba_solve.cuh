@@ -723,7 +723,8 @@ inline int solver_alloc(mvus_ba_ctx* h) {
         return fail(h, MVUS_ERR_UNSUPPORTED, "more than 2^26 spline unknowns per handle");
     MV_CUDA(h, h->D.alloc(nba * qq));
     MV_CUDA(h, h->E.alloc(nba * qq));
-    MV_CUDA(h, h->W.alloc(nba * h->q * h->ldw));
+    MV_CUDA(h, h->W.alloc((nba * h->q + 2 * K2_GUARD) * h->ldw));       // K2_GUARD rows in front of W~ (K2's window of
+    h->w_guard = (size_t)K2_GUARD * h->ldw;                             //   block 0 starts at control point -3): see Wp()
     MV_CUDA(h, h->Dw.alloc(nba * qq));
     MV_CUDA(h, h->Ew.alloc(nba * qq));
     MV_CUDA(h, h->Ww.alloc(nba * h->q * h->ldw));
@@ -754,38 +755,50 @@ inline int accumulate(mvus_ba_ctx* h) {
     MV_CUDA(h, cudaMemsetAsync(h->A.p, 0, h->A.bytes(), h->st));
     MV_CUDA(h, cudaMemsetAsync(h->D.p, 0, h->nb * qq * sizeof(double), h->st));
     MV_CUDA(h, cudaMemsetAsync(h->E.p, 0, h->nb * qq * sizeof(double), h->st));
-    MV_CUDA(h, cudaMemsetAsync(h->W.p, 0, (size_t)h->nb * h->q * h->ldw * sizeof(double), h->st));
-    if (h->n_tiles > 0) {
-        // tile order by time (see tile_key_kernel); spans move little between evaluations, but the sort is cheap
-        const int nt = h->n_tiles;
-        MV_CUDA(h, h->tile_key.alloc(nt));
-        MV_CUDA(h, h->tile_key2.alloc(nt));
-        MV_CUDA(h, h->tile_id.alloc(nt));
-        MV_CUDA(h, h->tile_perm.alloc(nt));
+    MV_CUDA(h, cudaMemsetAsync(h->Wp(), 0, (size_t)h->nb * h->q * h->ldw * sizeof(double), h->st));
+    if (h->n_chunks > 0) {
+        // chunk order by time (see chunk_key_kernel); spans move little between evaluations, but the sort is cheap
+        const int nch = h->n_chunks;
+        MV_CUDA(h, h->chunk_key.alloc(nch));
+        MV_CUDA(h, h->chunk_key2.alloc(nch));
+        MV_CUDA(h, h->chunk_id.alloc(nch));
+        MV_CUDA(h, h->chunk_perm.alloc(nch));
+        MV_CUDA(h, h->k2_queue.alloc(1));
         size_t tb = 0;
-        MV_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, h->tile_key.p, h->tile_key2.p, h->tile_id.p,
-                                                   h->tile_perm.p, nt, 0, 32, h->st));
+        MV_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, h->chunk_key.p, h->chunk_key2.p, h->chunk_id.p,
+                                                   h->chunk_perm.p, nch, 0, 32, h->st));
         MV_CUDA(h, h->sort_tmp.alloc(tb));
-        tile_key_kernel<<<(nt + 255) / 256, 256, 0, h->st>>>(h->span.p, h->tile_start.p, nt, h->tile_key.p, h->tile_id.p);
-        MV_CUDA(h, cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tb, h->tile_key.p, h->tile_key2.p, h->tile_id.p,
-                                                   h->tile_perm.p, nt, 0, 32, h->st));
+        const int blk_d = jblk_doubles(h->P);
+        chunk_key_kernel<<<(nch + 255) / 256, 256, 0, h->st>>>(h->J.p, blk_d, blk_d - 16, h->chunk_tile0.p, nch,
+                                                              h->chunk_key.p, h->chunk_id.p);
+        MV_CUDA(h, cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tb, h->chunk_key.p, h->chunk_key2.p, h->chunk_id.p,
+                                                   h->chunk_perm.p, nch, 0, 32, h->st));
+        MV_CUDA(h, cudaMemsetAsync(h->k2_queue.p, 0, sizeof(int), h->st));
         h->launches += 3;
-        if (h->P == 21) {
-            MV_CUDA(h, cudaFuncSetAttribute(accumulate_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2Cfg<21>::SMEM));
-            accumulate_kernel<21><<<h->n_tiles * K2Cfg<21>::SPLITS, K2Cfg<21>::THREADS, K2Cfg<21>::SMEM, h->st>>>(
-                h->J.p, h->r.p, h->span.p, h->tile_perm.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
-                h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
-        } else {
-            MV_CUDA(h, cudaFuncSetAttribute(accumulate_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K2Cfg<30>::SMEM));
-            accumulate_kernel<30><<<h->n_tiles * K2Cfg<30>::SPLITS, K2Cfg<30>::THREADS, K2Cfg<30>::SMEM, h->st>>>(
-                h->J.p, h->r.p, h->span.p, h->tile_perm.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p, h->N,
-                h->bw, h->ldw, h->A.p, bc, h->D.p, h->E.p, h->W.p);
-        }
-        h->launches++;
+        const int64_t n_rows = (int64_t)(h->nb + 1) * h->q;
+        if ((n_rows + 2 * K2_GUARD) * (int64_t)h->ldw >= ((int64_t)1 << 32))        // K2 flushes with 32-bit offsets
+            return fail(h, MVUS_ERR_UNSUPPORTED, "W~ larger than 2^32 entries per handle");
+        const size_t hb_n = (size_t)(n_rows + 2 * K2_GUARD) * K2_BAND;
+        MV_CUDA(h, h->Hb.alloc(hb_n));
+        MV_CUDA(h, cudaMemsetAsync(h->Hb.p, 0, hb_n * sizeof(double), h->st));
+        const int grid = h->sm_count;
+#define MV_K2(PP)                                                                                            \
+    do {                                                                                                     \
+        MV_CUDA(h, cudaFuncSetAttribute(accumulate_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                        (int)K2Cfg<PP>::SMEM));                                              \
+        accumulate_kernel<PP><<<grid, K2Cfg<PP>::THREADS, K2Cfg<PP>::SMEM, h->st>>>(                         \
+            h->J.p, h->chunk_perm.p, h->chunk_tile0.p, h->chunk_nt.p, nch, h->k2_queue.p, h->tile_cam.p,     \
+            h->tile_cnt.p, h->ldw, h->A.p, bc, h->Hb.p, h->W.p);                                                      \
+    } while (0)
+        if (h->P == 21) MV_K2(21); else MV_K2(30);
+#undef MV_K2
+        band_to_blocks_kernel<<<(int)((n_rows * (K2_HALF + 1) + 255) / 256), 256, 0, h->st>>>(
+            h->Hb.p + (size_t)K2_GUARD * K2_BAND, n_rows, h->q, h->D.p, h->E.p);
+        h->launches += 2;
     }
     if (h->M > 0 && (h->world <= 1 || h->rank == 0)) {      // parameter-only rows: counted once
         accumulate_motion_kernel<<<(int)((h->M + 127) / 128), 128, 0, h->st>>>(
-            h->r.p + 2 * h->N, h->mbase.p, h->mJ.p, h->M, h->bw, h->ldw, h->D.p, h->E.p, h->W.p);
+            h->r.p + 2 * h->N, h->mbase.p, h->mJ.p, h->M, h->bw, h->ldw, h->D.p, h->E.p, h->Wp());
         h->launches++;
     }
     MV_CUDA(h, cudaGetLastError());
@@ -803,7 +816,7 @@ inline int compute_diag(mvus_ba_ctx* h, bool full_everywhere = false) {
     const int64_t cnt = std::max<int64_t>(nbq, h->ncP);
     int64_t lo = 0, hi = h->nb;
     if (h->world > 1 && !full_everywhere) owner_range(h, h->rank, &lo, &hi);
-    diag_kernel<<<(int)((cnt + 255) / 256), 256, 0, h->st>>>(h->A.p, h->D.p, h->W.p, h->nc, h->Pc, nbq, h->q,
+    diag_kernel<<<(int)((cnt + 255) / 256), 256, 0, h->st>>>(h->A.p, h->D.p, h->Wp(), h->nc, h->Pc, nbq, h->q,
                                                             h->ldw, 3 * h->n_ctrl, lo * h->q, hi * h->q,
                                                             h->diag_c.p, h->diag_s.p, h->bs.p);
     h->launches++;
@@ -936,11 +949,11 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
         h->launches += 1;
         BcrView v{h->Dw.p, h->Ew.p, h->Ww.p, h->ZL.p, h->dlt_s.p, nb};
         if (h->desc.rs_bounds) {          // frozen columns must be zeroed in a private copy
-            MV_CUDA(h, cudaMemcpyAsync(h->Ww.p, h->W.p, (size_t)nbq * ldw * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+            MV_CUDA(h, cudaMemcpyAsync(h->Ww.p, h->Wp(), (size_t)nbq * ldw * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
             freeze_cols_kernel<<<(int)((nbq + 255) / 256), 256, 0, h->st>>>(h->Ww.p, nbq, ldw, h->nc, h->Pc, h->frozen.p);
             h->launches++;
         } else {
-            v.Worig = h->W.p;             // first touch of every block reads W~ directly: no 2|W~| copy pass
+            v.Worig = h->Wp();             // first touch of every block reads W~ directly: no 2|W~| copy pass
         }
         std::vector<int64_t> levels = bcr_eliminate(h, v, nb, true, fail_flag);
         launch_syrk(h, h->Ww.p, nbq, h->Sd.p);
@@ -966,7 +979,7 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
                 h->D.p + lo * qq, h->diag_s.p + lo * q, lam, nloc * q, q,
                 std::max<int64_t>(0, 3 * h->n_ctrl - lo * q), h->Dw.p + lo * qq);
             MV_CUDA(h, cudaMemcpyAsync(h->Ew.p + lo * qq, h->E.p + lo * qq, nloc * qq * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-            MV_CUDA(h, cudaMemcpyAsync(h->Ww.p + lo * wn, h->W.p + lo * wn, (size_t)nloc * wn * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+            MV_CUDA(h, cudaMemcpyAsync(h->Ww.p + lo * wn, h->Wp() + lo * wn, (size_t)nloc * wn * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
             h->launches++;
             if (h->desc.rs_bounds) {
                 freeze_cols_kernel<<<(int)((nloc * q + 255) / 256), 256, 0, h->st>>>(h->Ww.p + lo * wn, nloc * q, ldw, h->nc, h->Pc, h->frozen.p);

@@ -79,11 +79,12 @@ extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
                     &h->int_b, &h->knots, &h->spanpoly, &h->span_t0, &h->lut_t0, &h->lut_invh, &h->tau,
                     &h->x, &h->x_trial, &h->camprep, &h->r, &h->J, &h->mJ, &h->partial, &h->A, &h->D, &h->E,
                     &h->W, &h->Dw, &h->Ew, &h->Ww, &h->ZL, &h->Sd, &h->dlt_c, &h->dlt_s, &h->diag_c,
-                    &h->diag_s, &h->gvec, &h->xs, &h->scratch, &h->gt_out, &h->Dt, &h->ZLt, &h->dst, &h->bs})
+                    &h->diag_s, &h->gvec, &h->xs, &h->scratch, &h->gt_out, &h->Dt, &h->ZLt, &h->dst, &h->bs, &h->Hb})
         b->release();
     for (auto* b : {&h->row_off, &h->tile_start, &h->knot_off, &h->ctrl_off, &h->xoff, &h->lut_off}) b->release();
     for (auto* b : {&h->tile_cam, &h->tile_cnt, &h->ncoef, &h->deg, &h->lut_n, &h->lut, &h->tau_spl, &h->span,
-                    &h->mbase, &h->flag, &h->frozen, &h->tile_key, &h->tile_key2, &h->tile_id, &h->tile_perm})
+                    &h->mbase, &h->flag, &h->frozen, &h->chunk_tile0, &h->chunk_nt, &h->chunk_key, &h->chunk_key2,
+                    &h->chunk_id, &h->chunk_perm, &h->k2_queue})
         b->release();
     h->tau_flag.release();
     h->sort_tmp.release();
@@ -158,6 +159,18 @@ static int set_detections_core(mvus_ba_ctx* h, const int64_t* count, const doubl
             tcnt.push_back((int)std::min<int64_t>(TILE_DET, cam_ptr[i + 1] - s));
         }
     h->n_tiles = (int)tcam.size();
+    {   // K2 chunks: up to K2_CHUNK_TILES consecutive tiles of one camera
+        std::vector<int> c0, cn;
+        for (int t = 0; t < h->n_tiles;) {
+            int e = t + 1;
+            while (e < h->n_tiles && e - t < K2_CHUNK_TILES && tcam[e] == tcam[t]) ++e;
+            c0.push_back(t); cn.push_back(e - t);
+            t = e;
+        }
+        h->n_chunks = (int)c0.size();
+        MV_CUDA(h, upload(h->chunk_tile0, c0, h->st));
+        MV_CUDA(h, upload(h->chunk_nt, cn, h->st));
+    }
     MV_CUDA(h, upload(h->tile_cam, tcam, h->st));
     MV_CUDA(h, upload(h->tile_start, tstart, h->st));
     MV_CUDA(h, upload(h->tile_cnt, tcnt, h->st));
@@ -263,7 +276,7 @@ int mvus::evaluate(mvus_ba_ctx* h, const double* xd, bool want_j) {
                                                       h->height.p, h->camprep.p);
     h->launches++;
     if (want_j) {
-        MV_CUDA(h, h->J.alloc((size_t)2 * h->P * (h->N > 0 ? h->N : 1)));
+        MV_CUDA(h, h->J.alloc((size_t)(h->n_tiles > 0 ? h->n_tiles : 1) * (TILE_DET / 32) * jblk_doubles(h->P)));
         if (h->M > 0) {
             MV_CUDA(h, h->mJ.alloc((size_t)10 * h->M));
             MV_CUDA(h, h->mbase.alloc((size_t)h->M));
@@ -274,7 +287,7 @@ int mvus::evaluate(mvus_ba_ctx* h, const double* xd, bool want_j) {
     resjac_kernel<CAL, WJ><<<h->n_tiles, TILE_DET, 0, h->st>>>(                                         \
         h->sv, xd, h->camprep.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p,           \
         h->frame.p, h->xr.p, h->yr.p, h->obs_u.p, h->obs_v.p, h->desc.undist_points, h->desc.opt_sync,  \
-        h->desc.opt_rs, h->N, h->r.p, h->span.p, h->J.p, h->partial.p)
+        h->desc.opt_rs, h->N, h->r.p, h->J.p, h->partial.p)
         if (h->desc.opt_calib) { if (want_j) MV_LAUNCH_K1(true, true); else MV_LAUNCH_K1(true, false); }
         else { if (want_j) MV_LAUNCH_K1(false, true); else MV_LAUNCH_K1(false, false); }
 #undef MV_LAUNCH_K1
@@ -342,8 +355,14 @@ extern "C" int mvus_ba_residual_jacobian(mvus_ba_handle h, const double* x, doub
     rc = evaluate(h, h->x.p, true);
     if (rc) return rc;
     if (r) MV_CUDA(h, cudaMemcpyAsync(r, h->r.p, h->m * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    if (span && h->N) MV_CUDA(h, cudaMemcpyAsync(span, h->span.p, h->N * sizeof(int), cudaMemcpyDeviceToHost, h->st));
-    if (J && h->N) MV_CUDA(h, cudaMemcpyAsync(J, h->J.p, (size_t)2 * h->P * h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if ((span || J) && h->N) {          // de-block into the documented layout (column planes J[2P][N])
+        MV_CUDA(h, h->scratch.alloc((size_t)2 * h->P * h->N));
+        deblock_kernel<<<h->n_tiles, TILE_DET, 0, h->st>>>(h->J.p, h->P, h->tile_start.p, h->tile_cnt.p, h->N,
+                                                          h->scratch.p, h->span.p);
+        MV_CUDA(h, cudaGetLastError());
+        if (span) MV_CUDA(h, cudaMemcpyAsync(span, h->span.p, h->N * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+        if (J) MV_CUDA(h, cudaMemcpyAsync(J, h->scratch.p, (size_t)2 * h->P * h->N * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    }
     if (mbase && h->M) MV_CUDA(h, cudaMemcpyAsync(mbase, h->mbase.p, h->M * sizeof(int), cudaMemcpyDeviceToHost, h->st));
     if (mJ && h->M) MV_CUDA(h, cudaMemcpyAsync(mJ, h->mJ.p, (size_t)10 * h->M * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     MV_CUDA(h, cudaStreamSynchronize(h->st));
@@ -647,7 +666,7 @@ extern "C" int mvus_ba_normal_equations(mvus_ba_handle h, const double* x, doubl
         std::vector<double> D((size_t)nb * q * q), E((size_t)nb * q * q), W((size_t)nb * q * ldw);
         MV_CUDA(h, cudaMemcpy(D.data(), h->D.p, D.size() * sizeof(double), cudaMemcpyDeviceToHost));
         MV_CUDA(h, cudaMemcpy(E.data(), h->E.p, E.size() * sizeof(double), cudaMemcpyDeviceToHost));
-        MV_CUDA(h, cudaMemcpy(W.data(), h->W.p, W.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        MV_CUDA(h, cudaMemcpy(W.data(), h->Wp(), W.size() * sizeof(double), cudaMemcpyDeviceToHost));
         const int64_t nctrl = h->n_ctrl;
         if (Hss) {
             const int band = 2 * bw;

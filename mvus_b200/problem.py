@@ -98,8 +98,13 @@ class FlatProblem:
                  np.asarray(scene.rs, dtype=np.float64)[seq]]
         for i in seq:
             c = scene.cameras[i]
-            r = hostmath.matrix_to_rodrigues(c.R)
-            t = np.asarray(c.t, dtype=np.float64).reshape(3)
+            if c.R is None or c.t is None:
+                # a camera without a pose yet (main.py adds cameras one by one): only its time stamps and
+                # undistorted observations can be asked for (detection_to_global, common.py:105-127)
+                r, t = np.zeros(3), np.zeros(3)
+            else:
+                r = hostmath.matrix_to_rodrigues(c.R)
+                t = np.asarray(c.t, dtype=np.float64).reshape(3)
             if self.opt_calib:
                 parts.append(np.concatenate(([c.K[0, 0], c.K[1, 1], c.K[0, 2], c.K[1, 2]], r, t,
                                              np.asarray(c.d, dtype=np.float64).reshape(5))))

@@ -131,14 +131,16 @@ def test_dropin_installs_on_the_reference_module():
         common.Scene.remove_outliers = common.Scene._reference_remove_outliers
 
 
-@pytest.mark.parametrize('name,scramble', [('gs_plain', False), ('rs_F_gap', False), ('rs_F_gap', True), ('calib_KE', True)])
-def test_k2_sliding_window_model_matches_dense(name, scramble):
-    """tests/proto/k2_window_proto.py (the bookkeeping ba_k2.cuh implements: control point j in slot
-    j & 3, flush of the slots that leave the window, D as upper triangle, ordering by control point)
+@pytest.mark.parametrize('name,scramble,bw', [('gs_plain', False, 3), ('rs_F_gap', False, 4), ('rs_F_gap', True, 3),
+                                              ('calib_KE', True, 5), ('rs_bounds_dense', False, 6)])
+def test_k2_streaming_model_matches_dense(name, scramble, bw):
+    """tests/proto/k2_stream_proto.py (the bookkeeping ba_k2.cuh implements lane by lane: swizzled
+    32-detection blocks, column layout X|Y|Z|r|camera, column -> plane mapping of the fragment loads,
+    ping-pong phases, per-lane flush masks, D as upper triangle / E ordered by global row)
     == dense J^T J, J^T r of the reprojection rows.  `scramble` feeds the detections of each camera
     in a random order, i.e. arbitrary span sequences (jumps, returns, uncovered gaps)."""
     import helpers
-    from proto import k2_window_proto as k2
+    from proto import k2_stream_proto as k2
     from mvus_b200.problem import FlatProblem
     fl, truth, bakw = cases.make(name, det_per_cam=300)
     fp = FlatProblem(fl, fl.numCam, **bakw)
@@ -148,7 +150,6 @@ def test_k2_sliding_window_model_matches_dense(name, scramble):
     Jg = helpers.expand_jacobian(fp, span, J).toarray()[:2 * N]
     rr = np.asarray(r)[:2 * N]
     H, g = Jg.T @ Jg, Jg.T @ rr
-    bw = 3
     nb = (fp.n_ctrl + bw - 1) // bw
     q = 3 * bw
     out = None
@@ -166,6 +167,8 @@ def test_k2_sliding_window_model_matches_dense(name, scramble):
         # the kernels store abs(residual) rows with the sign folded into J, so r and J are consistent as they are
         out = k2.accumulate_camera(J[:P, order].T, J[P:, order].T, ru, rv, span[order], Pc, i, nc, bw, nb, out)
     A, bc, D, E, W = out
+    assert np.abs(W[nb * q:]).max() == 0.0 and np.abs(D[nb:]).max() == 0.0      # nothing lands in the ghost block
+    W = W[:nb * q]
     cam_cols = lambda i: np.array([i, nc + i, 2 * nc + i] + list(range(3 * nc + i * C, 3 * nc + (i + 1) * C)))
     ctrl_col = np.full(nb * q, -1)
     for s in range(fp.S):
