@@ -259,84 +259,101 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, int odd_o
 // S~ = sum over rows of W~^T W~ (lower-triangle tiles): the Schur complement's dense FP64
 // GEMM (ncP^2 * 3 n_ctrl flops = 200 GFLOP at config 4).  FP64 MMA (mma.sync m8n8k4 f64 -- the
 // only FP64 tensor instruction; tcgen05 has no f64 kind), 128x128 output tile per CTA, 16 warps
-// each owning a 32x32 warp tile = 4x4 fragments (32 accumulator doubles per thread), K chunks
-// of 16 rows staged in shared memory with a +4 padded leading dimension (fragment loads are
-// bank-conflict free: lane -> (k = lane&3, m = lane>>2) -> 4*k + m distinct 8-byte banks per
-// half warp), next chunk prefetched into registers while the current one is multiplied.
-// Split-K over row slabs, partial tiles reduced with FP64 RED.
-// History (profiles/r1_notes.md): v1 4x4 scalar micro-tiles 4.4 TFLOP/s (86 M bank conflicts),
-// v2 8x8 scalar micro-tiles 6.2 TFLOP/s (164 registers, 1 CTA/SM).
-constexpr int SY_T = 128, SY_K = 16, SY_LD = SY_T + 4;
+// each owning a 32x32 warp tile = 4x4 fragments (32 accumulator doubles per thread).  K chunks of
+// 16 rows go through a 4-stage cp.async ring in shared memory (+4 padded leading dimension: the
+// fragment loads are bank-conflict free, lane -> (k = lane&3, m = lane>>2) -> 4*k + m distinct
+// 8-byte banks per half warp) with ONE __syncthreads per chunk; rows of W~ are 8-byte aligned only
+// (ldw = ncP + 1 is odd), hence 8-byte copies, zero-filled past the slab / the last column.
+// Split-K over row slabs, partial tiles reduced with FP64 RED.  Only the ncP camera columns enter
+// the GEMM: the right-hand-side column (W~^T w_rhs, one row of S~) is a GEMV (wtw_rhs_kernel), so
+// that 576 = 18 x 32 columns need no padding strip.
+// History: v1 4x4 scalar micro-tiles 4.4 TFLOP/s, v2 8x8 scalar 6.2 TFLOP/s, v3 FP64 MMA with a
+// single-buffered register-prefetch pipeline 23 TFLOP/s issued (DMMA pipe 60 %; profiles/r1_notes.md).
+constexpr int SY_T = 128, SY_K = 16, SY_LD = SY_T + 4, SY_STAGES = 4;
+constexpr size_t SY_SMEM = (size_t)SY_STAGES * 2 * SY_K * SY_LD * sizeof(double);
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void sy_cp8(unsigned dst, const double* src, bool ok) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst), "l"(src), "r"(ok ? 8u : 0u) : "memory");
+}
 
 __global__ void __launch_bounds__(512)
-syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int slab, double* __restrict__ Sfull) {
-    __shared__ double As[SY_K][SY_LD], Bs[SY_K][SY_LD];
+syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, double* __restrict__ Sfull) {
+    extern __shared__ __align__(16) double sy_smem[];
     int p = blockIdx.x, ti = 0;
     while (p >= ti + 1) { p -= ti + 1; ++ti; }
     const int tj = p;
     const bool diag = (ti == tj);
     const int64_t r0 = (int64_t)blockIdx.y * slab;
     const int64_t r1 = r0 + slab < R ? r0 + slab : R;
+    const int nchunk = (int)((r1 - r0 + SY_K - 1) / SY_K);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wy = warp >> 2, wx = warp & 3;               // 4 x 4 warps of 32 x 32
+    // 4 x 4 warps of 32 x 32.  Warp w issues on scheduler w & 3: in a diagonal tile pair only the warp
+    // tiles wx <= wy work, so they are handed out in an order that spreads them over the four schedulers
+    // (with wx = w & 3 scheduler 0 had 4 working warps and scheduler 3 one: the CTA took as long as a full tile).
+    int wy = warp >> 2, wx = warp & 3;
+    if (diag) {
+        if (warp < 10) {                                   // the 10 lower warp tiles, row by row
+            wy = warp >= 6 ? 3 : warp >= 3 ? 2 : warp >= 1 ? 1 : 0;
+            wx = warp - wy * (wy + 1) / 2;
+        } else {                                           // the 6 idle ones (wx > wy)
+            const int idx = warp - 10;
+            wy = idx < 3 ? 0 : idx < 5 ? 1 : 2;
+            wx = idx < 3 ? idx + 1 : idx < 5 ? idx - 1 : 3;
+        }
+    }
     const int fk = lane & 3, fm = lane >> 2;               // fragment coordinates
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-    // warp tiles that only hold padding columns (last tile: ldw = 577 of 640) or lie strictly above
-    // the diagonal of a diagonal tile pair contribute nothing: they still stage data, but skip the MMAs
-    const bool warp_active = (ti * SY_T + wy * 32 < ldw) && (tj * SY_T + wx * 32 < ldw) && !(diag && wx > wy);
-    // each thread stages 4 elements of each panel per chunk: idx = tid + 512*k -> (row, col)
-    double pa[4], pb[4];
-    auto gload = [&](int64_t rr) {
+    // warp tiles that only hold padding columns (last tile) or lie strictly above the diagonal of a
+    // diagonal tile pair contribute nothing: they still help staging, but skip the MMAs
+    const bool warp_active = (ti * SY_T + wy * 32 < n) && (tj * SY_T + wx * 32 < n) && !(diag && wx > wy);
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sy_smem);
+    // each thread stages 4 elements of each panel per chunk: idx = tid + 512*k -> (row kk, column cc)
+    auto issue = [&](int c) {
+        const int st = c % SY_STAGES;
+        const unsigned sa = sbase + (unsigned)(st * 2 * SY_K * SY_LD) * 8u, sb = sa + (unsigned)(SY_K * SY_LD) * 8u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int idx = tid + k * 512;
             const int kk = idx >> 7, cc = idx & 127;
-            const int64_t row = rr + kk;
+            const int64_t row = r0 + (int64_t)c * SY_K + kk;
+            const bool inr = c < nchunk && row < r1;
             const int ca = ti * SY_T + cc, cb = tj * SY_T + cc;
-            const bool inr = row < r1;
-            pa[k] = (inr && ca < ldw) ? __ldg(Ww + row * ldw + ca) : 0.0;
-            pb[k] = (!diag && inr && cb < ldw) ? __ldg(Ww + row * ldw + cb) : 0.0;
+            const unsigned off = (unsigned)(kk * SY_LD + cc) * 8u;
+            sy_cp8(sa + off, inr && ca < n ? Ww + row * ldw + ca : Ww, inr && ca < n);
+            if (!diag) sy_cp8(sb + off, inr && cb < n ? Ww + row * ldw + cb : Ww, inr && cb < n);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto sstore = [&]() {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int idx = tid + k * 512;
-            const int kk = idx >> 7, cc = idx & 127;
-            As[kk][cc] = pa[k];
-            if (!diag) Bs[kk][cc] = pb[k];
-        }
-    };
-    gload(r0);
-    for (int64_t rr = r0; rr < r1; rr += SY_K) {
-        sstore();
-        __syncthreads();
-        if (rr + SY_K < r1) gload(rr + SY_K);
-        const double (*Bp)[SY_LD] = diag ? As : Bs;
+    for (int c = 0; c < SY_STAGES - 1; ++c) issue(c);
+    for (int c = 0; c < nchunk; ++c) {
+        asm volatile("cp.async.wait_group %0;" :: "n"(SY_STAGES - 2) : "memory");
+        __syncthreads();                       // chunk c has landed for everybody; stage (c - 1) % STAGES is free
+        issue(c + SY_STAGES - 1);
+        const double* As = sy_smem + (size_t)(c % SY_STAGES) * 2 * SY_K * SY_LD;
+        const double* Bp = diag ? As : As + SY_K * SY_LD;
         if (warp_active)
 #pragma unroll
-        for (int ks = 0; ks < SY_K; ks += 4) {
-            double a[4], b[4];
+            for (int ks = 0; ks < SY_K; ks += 4) {
+                double a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                a[i] = As[ks + fk][wy * 32 + i * 8 + fm];
-                b[i] = Bp[ks + fk][wx * 32 + i * 8 + fm];
+                for (int i = 0; i < 4; ++i) {
+                    a[i] = As[(ks + fk) * SY_LD + wy * 32 + i * 8 + fm];
+                    b[i] = Bp[(ks + fk) * SY_LD + wx * 32 + i * 8 + fm];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-        }
-        __syncthreads();
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -347,8 +364,33 @@ syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int slab, double*
                 const int row = ti * SY_T + wy * 32 + i * 8 + fm;
                 const int col = tj * SY_T + wx * 32 + j * 8 + fk * 2 + e;
                 const double v = acc[i][j][e];
-                if (row < ldw && col <= row && v != 0.0) atomicAdd(Sfull + (int64_t)row * ldw + col, v);
+                if (row < n && col <= row && v != 0.0) atomicAdd(Sfull + (int64_t)row * ldw + col, v);
             }
+}
+
+// S~[n][0..n) = sum over rows of W~[row][n] * W~[row][0..n): the right-hand-side row of the Schur system.
+// One warp per slab of rows, lane -> columns lane + 32 k (coalesced), split-K reduced with FP64 RED.
+__global__ void __launch_bounds__(256)
+wtw_rhs_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, double* __restrict__ Sfull) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t r0 = w * slab, r1 = r0 + slab < R ? r0 + slab : R;
+    if (r0 >= R) return;
+    constexpr int NC = 1152 / 32;
+    double acc[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) acc[k] = 0.0;
+    for (int64_t row = r0; row < r1; ++row) {
+        const double* wr = Ww + row * ldw;
+        const double g = wr[n];
+        if (g == 0.0) continue;
+#pragma unroll
+        for (int k = 0; k < NC; ++k)
+            if (lane + 32 * k < n) acc[k] += g * wr[lane + 32 * k];
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k)
+        if (lane + 32 * k < n && acc[k] != 0.0) atomicAdd(Sfull + (int64_t)n * ldw + lane + 32 * k, acc[k]);
 }
 
 // rs_bounds (common.py:655-660, scipy trf_bounds): active-set treatment of the box 0 <= rho <= 1.
@@ -886,16 +928,20 @@ inline void bcr_back(mvus_ba_ctx* h, const BcrView& v, const std::vector<int64_t
 
 inline void launch_syrk(mvus_ba_ctx* h, const double* Wrows, int64_t R, double* Sfull) {
     if (R <= 0) return;
-    const int ldw = h->ldw;
-    const int nts = (ldw + SY_T - 1) / SY_T, npairs = nts * (nts + 1) / 2;
-    // ~8 waves of CTAs over the SMs (one 512-thread CTA of 128 registers per SM; CTA durations differ by
-    // up to 16:6 active warp tiles, so 4 waves left a tail of most of a CTA duration), slabs a multiple of
-    // the K chunk
+    const int ldw = h->ldw, n = h->ncP;
+    const int nts = (n + SY_T - 1) / SY_T, npairs = nts * (nts + 1) / 2;
+    // ~8 waves of CTAs over the SMs (one 512-thread CTA per SM; CTA durations differ by up to 16:6 active
+    // warp tiles, so few waves leave a tail of most of a CTA duration), slabs a multiple of the K chunk
     int64_t nslab = std::max<int64_t>(1, (8 * h->sm_count + npairs - 1) / npairs);
     int slab = (int)std::max<int64_t>(256, ((R + nslab - 1) / nslab + SY_K - 1) / SY_K * SY_K);
     dim3 g(npairs, (unsigned)((R + slab - 1) / slab));
-    syrk_kernel<<<g, 512, 0, h->st>>>(Wrows, R, ldw, slab, Sfull);
-    h->launches++;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM); attr_set = true; }
+    syrk_kernel<<<g, 512, SY_SMEM, h->st>>>(Wrows, R, ldw, n, slab, Sfull);
+    const int rslab = 64;                                  // rows per warp of the right-hand-side GEMV
+    const int64_t nwarps = (R + rslab - 1) / rslab;
+    wtw_rhs_kernel<<<(int)((nwarps * 32 + 255) / 256), 256, 0, h->st>>>(Wrows, R, ldw, n, rslab, Sfull);
+    h->launches += 2;
 }
 
 // copy the chunk-head blocks of this rank (and its ghost) into the compact top-level arrays

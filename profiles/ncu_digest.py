@@ -16,7 +16,7 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'l1tex__t_requests_pipe_lsu_mem_global_op_red.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum',
         'lts__t_sector_hit_rate.pct', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
-        'smsp__inst_executed_pipe_fp64.sum', 'sm__inst_executed_pipe_fmaheavy.sum']
+        'sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active']
 d = dict(zip(hdr, zip(units, vals)))
 for k in want:
     if k in d:
