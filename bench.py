@@ -120,32 +120,98 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(sm)}
 
 
-def cpu_reference_run(a, steps, warmup):
-    """The reference's CPU path on a bounded sample of the workload: oracle port of
-    Scene.BA's least_squares call (2-point FD on the jac_BA pattern, TRF+LSMR), all host threads
-    BLAS wants.  Returns (Mdet/s, dict)."""
+def sample_flight(a):
+    """The bounded CPU sample of the workload: same settings (rolling shutter, distortion, motion F,
+    w = 1e4), a.sample_cams cameras x a.sample_det detections -- the size at which the UNMODIFIED
+    reference still runs (its jac_BA pattern is a dense int64 m x n array, common.py:610)."""
     from mvus_b200 import synth
-    from oracle import ba_oracle
     fl, _ = synth.make_flight(nc=a.sample_cams, det_per_cam=a.sample_det, rolling_shutter=True,
                               distortion=True, motion_type='F', motion_weights=1e4, uncovered=0.0)
-    prob = ba_oracle.Problem(fl, fl.numCam, **BA_KW)
-    N = int(sum(prob.N))
-    t0 = time.perf_counter()
-    A = prob.pattern_near3(prob.x0)
-    t_pat = time.perf_counter() - t0
+    return fl
+
+
+def cpu_reference_run(a, steps, warmup):
+    """The reference's CPU path on a bounded sample of the workload, all host threads BLAS wants.
+    kind "reference": the UNMODIFIED reference (oracle/_ref, the verbatim copy oracle/make_ref.py makes)
+    -- Scene.BA = jac_BA pattern + scipy least_squares(TRF, LSMR, 2-point FD) exactly as common.py:670;
+    kind "port": the oracle's restatement of that call, only when oracle/_ref did not travel.
+    BASELINE.md section 3 legs: (1) error_BA residual Mdet/s, (2) approx_derivative residual+Jacobian
+    Mdet/s, (3) LM iterations/s.  Returns (Mdet/s of leg 3, info dict, seconds, iterations)."""
+    import contextlib
+    import io
+    from oracle import ba_oracle, ref_shim
+    from scipy.optimize._numdiff import approx_derivative, group_columns
+    fl = sample_flight(a)
+    N = int(sum(d.shape[1] for d in fl.detections))
+    kw = dict(BA_KW)
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    if ref_shim.available():
+        kind = 'reference'
+        t0 = time.perf_counter()
+        with quiet:
+            fn, x0, A, _ = ref_shim.capture_ba(ref_shim.to_reference_scene(fl), fl.numCam, **kw)
+        t_pat = time.perf_counter() - t0                  # jac_BA (compute_visibility + pattern), common.py:665
+
+        def solve(max_nfev):
+            ref = ref_shim.to_reference_scene(fl)
+            with quiet:
+                return ref.BA(fl.numCam, max_iter=max_nfev, **kw)
+    else:
+        kind = 'port'
+        prob = ba_oracle.Problem(fl, fl.numCam, **kw)
+        x0, fn = prob.x0, prob.residual
+        t0 = time.perf_counter()
+        A = prob.pattern_near3(prob.x0)
+        t_pat = time.perf_counter() - t0
+
+        def solve(max_nfev):
+            return prob.shipped_solve(prob.x0, max_nfev=max_nfev, pattern=A)
+    n, m = len(x0), len(fn(x0))
+    ts = []
+    for _ in range(5):                                    # leg 1
+        t0 = time.perf_counter()
+        f0 = fn(x0)
+        ts.append(time.perf_counter() - t0)
+    t_res = float(np.median(ts))
+    groups = group_columns(A)
+    t0 = time.perf_counter()                              # leg 2: what least_squares does per Jacobian
+    approx_derivative(fn, x0, method='2-point', f0=f0, sparsity=(A, groups))
+    t_jac = time.perf_counter() - t0 + t_res
     if warmup:
-        prob.shipped_solve(prob.x0, max_nfev=2, pattern=A)
-    t0 = time.perf_counter()
-    res = prob.shipped_solve(prob.x0, max_nfev=steps + 1, pattern=A)
-    dt = time.perf_counter() - t0
+        solve(2)
+    t0 = time.perf_counter()                              # leg 3
+    res = solve(steps + 1)
+    dt = time.perf_counter() - t0 - (t_pat if kind == 'reference' else 0.0)     # (Scene.BA rebuilds the pattern)
     iters = max(res.nfev - 1, 1)
     val = N * iters / dt / 1e6
-    info = {'value': val, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
-            'sample': '%d cameras x %d detections (N=%d, n=%d, m=%d), same settings; %d LM iterations in %.2f s '
-                      '(%.3f LM it/s; jac_BA pattern %.2f s not included)' % (
-                          a.sample_cams, a.sample_det, N, prob.n, prob.m, iters, dt, iters / dt, t_pat),
-            'lm_iters_per_s': iters / dt, 'final_cost': float(res.cost)}
+    info = {'value': val, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': kind,
+            'sample': '%d cameras x %d detections (N=%d, n=%d, m=%d), same settings as the workload; %d LM iterations '
+                      '(nfev %d, njev %d, status %d) in %.2f s; jac_BA pattern %.2f s not included' % (
+                          a.sample_cams, a.sample_det, N, n, m, iters, res.nfev, res.njev, res.status, dt, t_pat),
+            'lm_iters_per_s': iters / dt, 'final_cost': float(res.cost),
+            'resid_mdet_per_s': N / t_res / 1e6, 'resid_jac_mdet_per_s': N / t_jac / 1e6,
+            'fd_colour_groups': int(groups.max()) + 1, 'pattern_s': t_pat}
     return val, info, dt, iters
+
+
+def gpu_on_sample(a, steps):
+    """Same-config pair of the CPU arm: the sample flight through the public API on this GPU."""
+    from mvus_b200 import ba
+    fl = sample_flight(a)
+    N = int(sum(d.shape[1] for d in fl.detections))
+    import contextlib
+    import io
+    out = {}
+    with contextlib.redirect_stdout(io.StringIO()):
+        ba.bundle_adjust(sample_flight(a), a.sample_cams, max_iter=3, ftol=0.0, xtol=0.0, gtol=0.0, **BA_KW)   # warm-up
+        t0 = time.perf_counter()
+        res = ba.bundle_adjust(fl, fl.numCam, max_iter=steps + 1, ftol=0.0, xtol=0.0, gtol=0.0, **BA_KW)
+        dt = time.perf_counter() - t0
+    it = max(res.nfev - 1, 1)
+    out = {'workload': '%d cameras x %d detections' % (a.sample_cams, a.sample_det), 'steps': it,
+           'gpu_e2e_value': N * it / dt / 1e6, 'gpu_e2e_seconds': dt,
+           'gpu_value': N * it / (res.stats['ms_total'] / 1e3) / 1e6, 'gpu_final_cost': float(res.cost), 'unit': UNIT}
+    return out
 
 
 def run_cfg5(a, rank, world, local):
@@ -211,7 +277,7 @@ def main():
         return run_cfg5(a, rank, world, local)
     cfg = {'workload': workload_name(a), 'cams': a.cams, 'det_per_cam': a.det, 'coef_per_axis': a.coef,
            'l2_policy': 'inputs (J planes >= 0.3 GB) exceed L2; no flush needed',
-           'parallelism': 'detections sharded by camera+time chunk over %d GPU(s), NCCL all-reduce of normal equations' % world}
+           'parallelism': 'detections sharded along the global time axis (owner ranges of the sharded solve) over %d GPU(s); NCCL: camera blocks all-reduced, spline-side halo rows reduced to their owner' % world}
 
     if a.impl == 'reference':
         if rank != 0:
@@ -241,7 +307,8 @@ def main():
     t_gen = time.perf_counter() - t0
     N_total = int(sum(d.shape[1] for d in fl.detections))
     if world > 1:
-        fl = shard.shard_scene(fl, rank, world)
+        # cut along the control-point ranges the ranks own in the sharded solve (halo-only exchange)
+        fl = shard.shard_scene(fl, rank, world, shard.shard_bounds(fl, world, motion_reg=BA_KW.get('motion_reg', False)))
     fp = FlatProblem(fl, fl.numCam, **BA_KW)
 
     # ---- device-resident timing -----------------------------------------------------------
@@ -265,7 +332,8 @@ def main():
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     steps_done = st.nfev - 1
-    ms = torch.tensor([st.ms_total, ms_k1, ms_k2, st.ms_resjac, st.ms_accum, st.ms_solve, st.ms_trial],
+    ms = torch.tensor([st.ms_total, ms_k1, ms_k2, st.ms_resjac, st.ms_accum, st.ms_solve, st.ms_trial,
+                       st.ms_syrk, st.ms_bcr, st.ms_reduce, st.ms_k2],
                       dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -282,11 +350,10 @@ def main():
     fp.unpack_into(fl, fp.x0)
     if world > 1:
         dist.barrier()
-    # two timed repetitions from the same start; the faster one is reported (host-side hiccups --
-    # page cache, allocator -- have moved a single repetition by 0.4 s on a fresh box), both are listed
+    # three timed repetitions from the same start; the MEDIAN is reported, all are listed
     import gc
-    e2e_all, e2e_hosts, e2e_info = [], [], None
-    for _rep in range(2):
+    e2e_all, e2e_hosts, e2e_infos = [], [], []
+    for _rep in range(3):
         fp.unpack_into(fl, fp.x0)
         gc.collect()                       # (the previous result's pinned arrays go back to the pool first)
         if world > 1:
@@ -300,11 +367,12 @@ def main():
             dist.all_reduce(dt_k, op=dist.ReduceOp.MAX)
         e2e_all.append(float(dt_k.item()))
         e2e_hosts.append(res_k.stats.get('host'))
-        if e2e_info is None or e2e_all[-1] <= min(e2e_all[:-1]):
-            e2e_info = {'nfev': int(res_k.nfev), 'host': res_k.stats.get('host'),
-                        'pinned_new': _cabi.POOL.new_bytes - pool0[0], 'pinned_reused': _cabi.POOL.reused_bytes - pool0[1]}
+        e2e_infos.append({'nfev': int(res_k.nfev), 'host': res_k.stats.get('host'),
+                          'pinned_new': _cabi.POOL.new_bytes - pool0[0], 'pinned_reused': _cabi.POOL.reused_bytes - pool0[1]})
         del res_k
-    dt_e2e = min(e2e_all)
+    k_med = int(np.argsort(e2e_all)[len(e2e_all) // 2])
+    e2e_info = e2e_infos[k_med]
+    dt_e2e = e2e_all[k_med]
     e2e_steps = max(e2e_info['nfev'] - 1, 1)
     e2e_val = N_total * e2e_steps / dt_e2e / 1e6
     h2d = (3 * fp.N * 8 + fp.n * 8) / e2e_steps
@@ -321,27 +389,59 @@ def main():
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
+    # FP64 tensor peak: MEASURED_PEAKS.json has no FP64 entry; measured on this pool's B200 with
+    # profiles/micro/dmma_bench.cu (profiles/r2_fp64_bars.txt): 36.8 TFLOP/s for every mma.sync f64 shape
+    fp64_peak = float(peaks.get('fp64_tensor_tflops', 36.8))
+    fp64_src = ('measured (MEASURED_PEAKS.json)' if 'fp64_tensor_tflops' in peaks else
+                'measured with profiles/micro/dmma_bench.cu (profiles/r2_fp64_bars.txt); MEASURED_PEAKS.json has no FP64 entry')
     P = fp.P
     N_loc = fp.N
+    n_solves = max(int(st.lm_iterations), 1)
+    ncP = fp.nc * fp.Pc
+    rows_w = 3 * fp.n_ctrl / world                        # rows of W~ per rank
     k1_bytes = N_loc * (24 + 16 + 4 + 16 * P)            # 380 B/det (P=21)
     k2_bytes = N_loc * (16 + 4 + 16 * P)                 # 356 B/det
-    phases = {'resjac_K1': {'ms': ms[1], 'algorithmic_GBps': k1_bytes / ms[1] / 1e6, 'bytes_per_det': 44 + 16 * P},
-              'accumulate_K2': {'ms': ms[2], 'algorithmic_GBps': k2_bytes / ms[2] / 1e6, 'bytes_per_det': 20 + 16 * P},
-              'solve_share_ms': ms[5], 'resjac_share_ms': ms[3], 'accum_share_ms': ms[4], 'trial_share_ms': ms[6]}
-    dom = 'resjac_K1' if ms[3] >= ms[4] else 'accumulate_K2'
-    ach = phases[dom]['algorithmic_GBps']
-    # DRAM traffic per detection from the round's `ncu --set full` captures at config 4
-    # (profiles/r1_ncu_full_cfg4_{resjac,accumulate_mma}.raw.csv: dram__bytes_read.sum + write.sum over
-    # 64 000 042 detections, P = 21); None for other P
-    ncu_bytes_per_det = {'resjac_K1': 411.0, 'accumulate_K2': 445.0} if P == 21 else {}
-    traffic = ncu_bytes_per_det.get(dom)
-    roof = {'bound': 'hbm', 'kernel': dom, 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-            'traffic': None if traffic is None else traffic * N_loc / 1e9, 'traffic_unit': 'GB per launch (ncu, config 4 capture scaled by detections)',
-            'peak_source': peak_src,
-            'note': 'per-rank detections x %d B/det / CUDA-event time of the kernel run alone (3 reps)' % phases[dom]['bytes_per_det'],
-            'other_kernel': {'kernel': 'resjac_K1' if dom != 'resjac_K1' else 'accumulate_K2',
-                             'achieved': phases['resjac_K1' if dom != 'resjac_K1' else 'accumulate_K2']['algorithmic_GBps'],
-                             'frac': phases['resjac_K1' if dom != 'resjac_K1' else 'accumulate_K2']['algorithmic_GBps'] / peak}}
+    bcr_bytes = 2.0 * rows_w * (ncP + 1) * 8             # one read + one write of W~ per solve
+    syrk_flop = float(ncP) * (ncP + 1) * rows_w          # lower triangle of W~^T W~: n (n+1) / 2 x 2 flop x rows
+    ms_syrk1, ms_bcr1 = ms[7] / n_solves, ms[8] / n_solves
+    # DRAM traffic per launch from this round's `ncu --set full` captures (profiles/r2_ncu_traffic.json, written by
+    # profiles/ncu_traffic.py from the .ncu-rep files: dram__bytes_read.sum + dram__bytes_write.sum), scaled by the
+    # rank's share of the config-4 problem; None for other problem shapes
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r2_ncu_traffic.json')))
+        if P == 21 and a.workload == 'cfg4':
+            traffic = {k: v['dram_bytes'] * (N_loc / v['detections']) / 1e9 for k, v in tj.items()}
+    except Exception:
+        pass
+    phases = {'resjac_K1': {'ms': ms[1], 'share_ms': ms[3], 'bound': 'hbm', 'achieved': k1_bytes / ms[1] / 1e6, 'unit': 'GB/s',
+                            'frac': k1_bytes / ms[1] / 1e6 / peak, 'bytes_per_det': 44 + 16 * P, 'traffic': traffic.get('resjac_K1')},
+              'accumulate_K2': {'ms': ms[2], 'share_ms': ms[10], 'bound': 'hbm', 'achieved': k2_bytes / ms[2] / 1e6, 'unit': 'GB/s',
+                                'frac': k2_bytes / ms[2] / 1e6 / peak, 'bytes_per_det': 20 + 16 * P,
+                                'traffic': traffic.get('accumulate_K2'),
+                                'note': 'K2 + K2m + memsets of W~/D/E + chunk sort + band_to_blocks, run alone (3 reps)'},
+              'schur_syrk_K3': {'ms': ms_syrk1, 'share_ms': ms[7], 'bound': 'tensor', 'achieved': syrk_flop / ms_syrk1 / 1e9 if ms_syrk1 else None,
+                                'unit': 'TFLOP/s', 'frac': syrk_flop / ms_syrk1 / 1e9 / fp64_peak if ms_syrk1 else None,
+                                'flop_per_launch': syrk_flop, 'traffic': traffic.get('schur_syrk_K3'),
+                                'note': 'FP64 mma.sync (DMMA); useful flops = lower triangle n(n+1) x rows; per linear solve'},
+              'cyclic_reduction_K3': {'ms': ms_bcr1, 'share_ms': ms[8], 'bound': 'hbm', 'achieved': bcr_bytes / ms_bcr1 / 1e6 if ms_bcr1 else None,
+                                      'unit': 'GB/s', 'frac': bcr_bytes / ms_bcr1 / 1e6 / peak if ms_bcr1 else None,
+                                      'bytes_per_launch': bcr_bytes, 'note': 'all elimination levels of one solve; 2 |W~|'},
+              'solve_share_ms': ms[5], 'resjac_share_ms': ms[3], 'accum_share_ms': ms[4], 'reduce_share_ms': ms[9],
+              'trial_share_ms': ms[6], 'linear_solves': n_solves}
+    kernels = ['resjac_K1', 'accumulate_K2', 'schur_syrk_K3', 'cyclic_reduction_K3']
+    dom = max(kernels, key=lambda k: phases[k]['share_ms'])          # the kernel with the largest share of the timed region
+    pd = phases[dom]
+    roof = {'bound': pd['bound'], 'kernel': dom, 'achieved': pd['achieved'], 'peak': peak if pd['bound'] == 'hbm' else fp64_peak,
+            'unit': pd['unit'], 'frac': pd['frac'], 'traffic': pd.get('traffic'),
+            'traffic_unit': 'GB per launch (ncu dram__bytes_read+write of this round, profiles/r2_ncu_traffic.json)',
+            'peak_source': peak_src if pd['bound'] == 'hbm' else fp64_src,
+            'share_of_step': pd['share_ms'] / ms[0],
+            'note': 'dominant kernel = largest share of the timed region (CUDA events inside the library)',
+            'other_kernels': [{'kernel': k, 'bound': phases[k]['bound'], 'achieved': phases[k]['achieved'], 'unit': phases[k]['unit'],
+                               'frac': phases[k]['frac'], 'share_of_step': phases[k]['share_ms'] / ms[0],
+                               'traffic': phases[k].get('traffic')} for k in kernels if k != dom],
+            'hbm_peak': peak, 'hbm_peak_source': peak_src, 'fp64_tensor_peak': fp64_peak}
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps_done, 'warmup': a.warmup,
             'ms_per_step': ms[0] / max(steps_done, 1), 'higher_is_better': True, 'scaling': 'strong',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
@@ -349,12 +449,17 @@ def main():
             'resid_jac_mdet_per_s': N_total / (ms[1] / 1e3) / 1e6,
             'roofline': roof, 'phases': phases, 'clocks': clocks,
             'e2e': {'value': e2e_val, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                    'seconds': dt_e2e, 'seconds_all': e2e_all, 'host_phases_all': e2e_hosts, 'steps': e2e_steps, 'host_phases_ms': e2e_info['host'],
+                    'seconds': dt_e2e, 'seconds_all': e2e_all, 'reported': 'median of %d repetitions' % len(e2e_all), 'host_phases_all': e2e_hosts, 'steps': e2e_steps, 'host_phases_ms': e2e_info['host'],
                     'pinned_new_bytes': e2e_info['pinned_new'], 'pinned_reused_bytes': e2e_info['pinned_reused']},
             'gpu_launches': int(st.launches), 'linear_solves': int(st.lm_iterations), 'final_cost': st.cost, 'cost0': st.cost0,
             'workload_gen_s': t_gen}
     if world == 1 and not a.no_cpu_baseline:
         _, info, _, _ = cpu_reference_run(a, 9, 1)
+        try:
+            info['same_config'] = gpu_on_sample(a, 9)        # GPU and CPU on the SAME sample
+            info['same_config']['cpu_value'] = info['value']
+        except Exception as e:                               # (never lose the bench line over the side measurement)
+            info['same_config'] = {'error': repr(e)}
         line['cpu_baseline'] = info
     print(json.dumps(line))
     if world > 1:

@@ -82,6 +82,10 @@ typedef struct mvus_ba_stats {
     double  ms_trial;        /* summed device time in residual-only evaluations           */
     int32_t launches;        /* kernels launched by this library during the solve         */
     int32_t n_resjac;        /* number of K1(with J) launches timed in ms_resjac          */
+    double  ms_syrk;         /* of ms_solve: the Schur-complement SYRK (+ rhs GEMV)       */
+    double  ms_bcr;          /* of ms_solve: cyclic-reduction levels (elimination)        */
+    double  ms_reduce;       /* of ms_accum: multi-GPU exchange of the normal equations   */
+    double  ms_k2;           /* of ms_accum: K2 + K2m (with their memsets)                */
 } mvus_ba_stats;
 
 const char* mvus_ba_version(void);
@@ -191,6 +195,14 @@ int mvus_ba_normal_equations(mvus_ba_handle h, const double* x, double* A, doubl
  * and the normal equations are summed over ranks. */
 int mvus_ba_nccl_unique_id(char id_out[128]);
 int mvus_ba_comm_init(mvus_ba_handle h, int32_t world_size, int32_t rank, const char id[128]);
+
+/* Control-point bounds of the block ranges the ranks of a world_size-GPU solve own
+ * (bounds[world_size + 1], bounds[0] = 0, bounds[world_size] = number of control points).  A
+ * detection whose knot span (index of its last active control point at the start parameters)
+ * lies in [bounds[r], bounds[r+1]) belongs on rank r: the exchange of the normal equations then
+ * only moves the 3-control-point halos at the range boundaries.  Any other
+ * partition of the detections stays correct, it only moves more.  Needs set_splines only. */
+int mvus_ba_shard_bounds(mvus_ba_handle h, int32_t world_size, int64_t* bounds);
 
 /* Timing helper for benchmarks: run `reps` back-to-back residual+Jacobian evaluations
  * (K1 + K1m) at x on the handle's stream, return the mean device ms (CUDA events). */

@@ -29,7 +29,9 @@ class BAStats(ctypes.Structure):
                 ('status', ctypes.c_int32), ('lm_iterations', ctypes.c_int32),
                 ('ms_total', ctypes.c_double), ('ms_resjac', ctypes.c_double),
                 ('ms_accum', ctypes.c_double), ('ms_solve', ctypes.c_double),
-                ('ms_trial', ctypes.c_double), ('launches', ctypes.c_int32), ('n_resjac', ctypes.c_int32)]
+                ('ms_trial', ctypes.c_double), ('launches', ctypes.c_int32), ('n_resjac', ctypes.c_int32),
+                ('ms_syrk', ctypes.c_double), ('ms_bcr', ctypes.c_double), ('ms_reduce', ctypes.c_double),
+                ('ms_k2', ctypes.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -39,7 +41,7 @@ EXPORTS = ['mvus_ba_version', 'mvus_ba_create', 'mvus_ba_destroy', 'mvus_ba_last
            'mvus_ba_set_detections', 'mvus_ba_set_detections_rows', 'mvus_ba_set_splines', 'mvus_ba_dims', 'mvus_ba_residual',
            'mvus_ba_residual_jacobian', 'mvus_ba_solve', 'mvus_ba_detections_global',
            'mvus_ba_normal_equations', 'mvus_ba_global_traj', 'mvus_ba_spline_to_traj', 'mvus_ba_visibility', 'mvus_ba_host_alloc',
-           'mvus_ba_host_free', 'mvus_ba_nccl_unique_id', 'mvus_ba_comm_init',
+           'mvus_ba_host_free', 'mvus_ba_nccl_unique_id', 'mvus_ba_comm_init', 'mvus_ba_shard_bounds',
            'mvus_ba_time_resjac', 'mvus_ba_time_accumulate']
 
 _lib = None
@@ -83,6 +85,7 @@ def load():
     lib.mvus_ba_host_free.restype = None
     lib.mvus_ba_nccl_unique_id.argtypes = [ctypes.c_char_p]
     lib.mvus_ba_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p]
+    lib.mvus_ba_shard_bounds.argtypes = [ctypes.c_void_p, ctypes.c_int32, _lp]
     lib.mvus_ba_time_resjac.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int32, _dp]
     lib.mvus_ba_time_accumulate.argtypes = [ctypes.c_void_p, ctypes.c_int32, _dp]
     _lib = lib
@@ -203,6 +206,12 @@ class Handle:
 
     def comm_init(self, world, rank, uid):
         self._check(self.lib.mvus_ba_comm_init(self.h, world, rank, uid))
+
+    def shard_bounds(self, world):
+        """Control-point bounds of the ranks' block ranges (mvus_ba_shard_bounds)."""
+        b = np.zeros(world + 1, dtype=np.int64)
+        self._check(self.lib.mvus_ba_shard_bounds(self.h, world, _l(b)))
+        return b
 
     def residual(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -64,6 +64,8 @@ struct mvus_ba_ctx {
     std::string err;
     cudaStream_t st = nullptr;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t evs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // sub-phase timers of the solve / accumulate
+    double ms_syrk = 0.0, ms_bcr = 0.0, ms_reduce = 0.0, ms_k2 = 0.0;
     int sm_count = 148;
 
     // sizes
@@ -117,6 +119,8 @@ struct mvus_ba_ctx {
 
     // multi-GPU
     int world = 1, rank = 0;
+    mvus::DevBuf<int> touch;             // touched super-block ranges of all ranks (reduce_normal_equations)
+    int64_t halo_blocks = 0;             // super-blocks moved by the last normal-equation exchange (diagnostic)
     void* nccl_comm = nullptr;
 };
 

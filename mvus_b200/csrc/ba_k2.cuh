@@ -248,6 +248,7 @@ accumulate_kernel(const double* __restrict__ Jb, const int* __restrict__ chunk_p
     for (int k = 0; k < Cfg::NPAIR; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
 
     int camoff = 0;      // cam * PC of the current chunk
+    int b_min = 0x7fffffff, b_max = -1;      // blocks of four spans this warp has seen (multi-GPU: the touched rows)
     // ---- flush of the entries selected by `m` (bits as above) for the window of block `blk` in phase `ph`.
     //      Rows 3 (4 blk - 3) + cr >= -K2_GUARD always, and <= n_rows - 1 for every span K1 can emit, so there are
     //      no bounds checks: an entry is its bit, a != 0 test, one add for the offset and the RED.
@@ -350,6 +351,7 @@ accumulate_kernel(const double* __restrict__ Jb, const int* __restrict__ chunk_p
                         ph = partial ? (ph ^ 1) : 0;
                     } else ph = 0;
                     cur_b = bseg;
+                    if (bseg >= 0) { b_min = min(b_min, bseg); b_max = max(b_max, bseg); }
                 }
                 if (bseg >= 0) {
                     // ---- rank-2n update of the segment [start, end): u rows then v rows along k
@@ -394,6 +396,7 @@ accumulate_kernel(const double* __restrict__ Jb, const int* __restrict__ chunk_p
         if (cur_b >= 0) flush(mX | mY | mZ, cur_b, ph);
         flush_camera();
     }
+    if (lane == 0 && b_max >= 0) { atomicMin(queue + 1, b_min); atomicMax(queue + 2, b_max); }
 }
 
 }  // namespace mvus

@@ -11,6 +11,7 @@
 // the trial costs are all-reduced so that every rank takes the same accept / reject decision.
 #pragma once
 #include <dlfcn.h>
+#include <climits>
 #include "ba_ctx.cuh"
 
 namespace mvus {
@@ -80,8 +81,14 @@ inline void owner_range(const mvus_ba_ctx* h, int r, int64_t* lo, int64_t* hi) {
 
 // Sum the per-rank normal equations.  Camera blocks (small) are all-reduced.  The spline-side
 // arrays D, E, W~ (2.8 GB at config 4) are only needed by the rank that owns the block range in
-// the sharded solve, so each range is REDUCED TO ITS OWNER (grouped ncclReduce: half the wire
-// traffic of an all-reduce); `full` forces an all-reduce (diagnostic entry point).
+// the sharded solve, and a rank only has non-zero rows where its own detections (and the motion
+// rows it owns) put them: K2 records the smallest / largest block of four spans it saw, the ranks
+// exchange those TOUCHED ranges (one tiny all-reduce), and for every owner s only the hull of
+// "rows touched by another rank inside s's range" is reduced to s (grouped ncclReduce; ranks
+// without a contribution there add zeros).  With detections sharded by time along the owner
+// ranges (mvus_b200/shard.py, mvus_ba_shard_bounds) that hull is the 3-control-point halo at the
+// range boundaries; with any other sharding it grows up to the whole range and stays correct.
+// `full` forces an all-reduce of everything (diagnostic entry point).
 inline int reduce_normal_equations(mvus_ba_ctx* h, bool full) {
     if (h->world <= 1) return MVUS_OK;
     const size_t qq = (size_t)h->q * h->q, wn = (size_t)h->q * h->ldw;
@@ -94,17 +101,56 @@ inline int reduce_normal_equations(mvus_ba_ctx* h, bool full) {
         if (!rc) rc = nccl_sum(h, h->Wp(), (size_t)h->nb * wn);
         return rc;
     }
+    // ---- touched super-block range of every rank: [tlo, thi] (inclusive), empty if tlo > thi
+    const int W = h->world;
+    std::vector<int> mine(2 * W, INT_MIN), all(2 * W, INT_MIN);
+    {
+        int kq[3] = {0, 0x7fffffff, -1};
+        if (h->n_chunks > 0 && h->k2_queue.p)
+            MV_CUDA(h, cudaMemcpyAsync(kq, h->k2_queue.p, sizeof(kq), cudaMemcpyDeviceToHost, h->st));
+        MV_CUDA(h, cudaStreamSynchronize(h->st));
+        int64_t tlo = h->nb, thi = -1;
+        if (kq[2] >= 0) {                                  // K2: control points 4 bmin - 3 .. 4 bmax + 3
+            tlo = std::max<int64_t>(0, (4 * (int64_t)kq[1] - 3)) / h->bw;
+            thi = std::min<int64_t>(h->nb - 1, (4 * (int64_t)kq[2] + 3) / h->bw);
+        }
+        if (h->M > 0) {                                    // motion rows of the own range reach <= 6 control points further
+            int64_t lo, hi;
+            owner_range(h, h->rank, &lo, &hi);
+            if (hi > lo) { tlo = std::min(tlo, lo); thi = std::max(thi, std::min<int64_t>(h->nb - 1, hi + 6 / h->bw + 1)); }
+        }
+        mine[2 * h->rank] = -(int)tlo;
+        mine[2 * h->rank + 1] = (int)thi;
+    }
+    MV_CUDA(h, h->touch.alloc(2 * W));
+    MV_CUDA(h, cudaMemcpyAsync(h->touch.p, mine.data(), 2 * W * sizeof(int), cudaMemcpyHostToDevice, h->st));
+    if (api.AllReduce(h->touch.p, h->touch.p, 2 * W, 2 /*ncclInt32*/, 2 /*ncclMax*/, h->nccl_comm, h->st) != 0)
+        return fail(h, MVUS_ERR_NCCL, "ncclAllReduce(touched ranges) failed");
+    MV_CUDA(h, cudaMemcpyAsync(all.data(), h->touch.p, 2 * W * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    MV_CUDA(h, cudaStreamSynchronize(h->st));
     int e = api.GroupStart();
-    for (int r = 0; r < h->world && e == 0; ++r) {
+    int64_t moved = 0;
+    for (int s = 0; s < W && e == 0; ++s) {
         int64_t lo, hi;
-        owner_range(h, r, &lo, &hi);
-        if (hi <= lo) continue;
-        const size_t nblk = (size_t)(hi - lo);
-        e = api.Reduce(h->D.p + lo * qq, h->D.p + lo * qq, nblk * qq, NCCL_FLOAT64, NCCL_SUM, r, h->nccl_comm, h->st);
-        if (!e) e = api.Reduce(h->E.p + lo * qq, h->E.p + lo * qq, nblk * qq, NCCL_FLOAT64, NCCL_SUM, r, h->nccl_comm, h->st);
-        if (!e) e = api.Reduce(h->Wp() + lo * wn, h->Wp() + lo * wn, nblk * wn, NCCL_FLOAT64, NCCL_SUM, r, h->nccl_comm, h->st);
+        owner_range(h, s, &lo, &hi);
+        if (s == W - 1) hi = h->nb;
+        int64_t hlo = hi, hhi = lo;                        // hull of foreign touched blocks inside [lo, hi)
+        for (int r = 0; r < W; ++r) {
+            if (r == s) continue;
+            const int64_t tlo = -(int64_t)all[2 * r], thi = all[2 * r + 1];
+            if (tlo > thi) continue;
+            const int64_t a = std::max(tlo, lo), b = std::min(thi + 1, hi);
+            if (a < b) { hlo = std::min(hlo, a); hhi = std::max(hhi, b); }
+        }
+        if (hhi <= hlo) continue;
+        const size_t nblk = (size_t)(hhi - hlo);
+        moved += (int64_t)nblk;
+        e = api.Reduce(h->D.p + hlo * qq, h->D.p + hlo * qq, nblk * qq, NCCL_FLOAT64, NCCL_SUM, s, h->nccl_comm, h->st);
+        if (!e) e = api.Reduce(h->E.p + hlo * qq, h->E.p + hlo * qq, nblk * qq, NCCL_FLOAT64, NCCL_SUM, s, h->nccl_comm, h->st);
+        if (!e) e = api.Reduce(h->Wp() + hlo * wn, h->Wp() + hlo * wn, nblk * wn, NCCL_FLOAT64, NCCL_SUM, s, h->nccl_comm, h->st);
     }
     const int e2 = api.GroupEnd();
+    h->halo_blocks = moved;
     if (e || e2) return fail(h, MVUS_ERR_NCCL, "grouped ncclReduce of the normal equations failed");
     return MVUS_OK;
 }
@@ -165,5 +211,24 @@ extern "C" int mvus_ba_comm_init(mvus_ba_handle h, int32_t world_size, int32_t r
     h->nccl_comm = cc.comm;
     h->world = world_size;
     h->rank = rank;
+    return MVUS_OK;
+}
+
+
+// Control-point bounds of the block ranges the ranks of a `world_size`-GPU solve own (bounds[world_size + 1],
+// bounds[0] = 0, bounds[world_size] = number of control points): detections whose knot span falls in
+// [bounds[r], bounds[r+1]) belong on rank r (mvus_b200/shard.py), so that the normal-equation exchange only moves
+// the halo rows at the range boundaries.  Needs mvus_ba_set_splines only.
+extern "C" int mvus_ba_shard_bounds(mvus_ba_handle h, int32_t world_size, int64_t* bounds) {
+    if (!h || !bounds || world_size < 1) return mvus::fail(h, MVUS_ERR_ARG, "bad argument");
+    if (!h->have_spl) return mvus::fail(h, MVUS_ERR_ARG, "set_splines first");
+    int bw = 3;
+    int64_t nb = 0, Bc = 1;
+    const int rc = mvus::solver_dims(h, world_size, &bw, &nb, &Bc);
+    if (rc) return rc;
+    const int64_t nchunks = nb / Bc;
+    for (int r = 0; r <= world_size; ++r)
+        bounds[r] = std::min<int64_t>(h->n_ctrl, nchunks * r / world_size * Bc * bw);
+    bounds[world_size] = h->n_ctrl;
     return MVUS_OK;
 }

@@ -21,6 +21,7 @@
 namespace mvus {
 
 int evaluate(mvus_ba_ctx* h, const double* xd, bool want_j);
+inline void owner_range(const mvus_ba_ctx* h, int r, int64_t* lo, int64_t* hi);    // ba_nccl.cuh
 
 constexpr int QMAX = 18;          // 3 * max control points per super-block (bw <= 6)
 constexpr double DIAG_MIN = 1e-6, DIAG_MAX = 1e32, DIAG_FLOOR_FRAC = 1e-2;
@@ -28,12 +29,12 @@ constexpr double DIAG_MIN = 1e-6, DIAG_MAX = 1e32, DIAG_FLOOR_FRAC = 1e-2;
 // K2m: motion rows -> spline block only.  One thread per sample.
 __global__ void accumulate_motion_kernel(const double* __restrict__ r_motion, const int* __restrict__ mbase,
                                          const double* __restrict__ mJ, int64_t M, int bw, int ldw,
-                                         double* __restrict__ D, double* __restrict__ E,
-                                         double* __restrict__ W) {
+                                         int64_t c_lo, int64_t c_hi, double* __restrict__ D,
+                                         double* __restrict__ E, double* __restrict__ W) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= M) return;
     const int base = mbase[j];
-    if (base < 0) return;
+    if (base < 0 || base < c_lo || base >= c_hi) return;    // (multi-GPU: rows of another rank's control points)
     const int q = 3 * bw;
     double fa[3], fc[7];
     for (int k = 0; k < 3; ++k) fa[k] = mJ[(int64_t)k * M + j];
@@ -720,9 +721,10 @@ __global__ void gradient_kernel(const double* __restrict__ bc, const double* __r
 
 // ------------------------------------------------------------------------------------------
 // Host orchestration
-inline int solver_alloc(mvus_ba_ctx* h) {
-    // super-block width: reprojection rows touch 4 consecutive control points (bw >= 3);
-    // a motion row touches up to `spread` consecutive ones (bw >= spread - 1).
+// Super-block structure of the spline block for a given world size: bw control points per super-block
+// (reprojection rows touch 4 consecutive control points -> bw >= 3; a motion row touches up to `spread`
+// consecutive ones -> bw >= spread - 1), nb super-blocks, chunk size Bc of the sharded solve.
+inline int solver_dims(mvus_ba_ctx* h, int world, int* bw_out, int64_t* nb_out, int64_t* Bc_out) {
     int spread = 4;
     if (h->M > 0) {
         std::vector<double> tau; std::vector<int> spl; std::vector<unsigned char> fl;
@@ -746,15 +748,21 @@ inline int solver_alloc(mvus_ba_ctx* h) {
     }
     if (spread > 7) return fail(h, MVUS_ERR_UNSUPPORTED,
                                 "a motion-prior row touches more than 7 consecutive control points");
-    h->bw = std::max(3, spread - 1);
-    h->q = 3 * h->bw;
-    h->nb = (h->n_ctrl + h->bw - 1) / h->bw;
-    h->Bc = 1;
-    if (h->world > 1) {
+    const int bw = std::max(3, spread - 1);
+    int64_t nb = (h->n_ctrl + bw - 1) / bw, Bc = 1;
+    if (world > 1) {
         // chunk size for the sharded solve: power of two, ~8 chunks per rank, >= 1
-        while (h->Bc * 2 * 8 * h->world <= h->nb) h->Bc *= 2;
-        h->nb = (h->nb + h->Bc - 1) / h->Bc * h->Bc;       // padded with decoupled identity blocks
+        while (Bc * 2 * 8 * world <= nb) Bc *= 2;
+        nb = (nb + Bc - 1) / Bc * Bc;                       // padded with decoupled identity blocks
     }
+    *bw_out = bw; *nb_out = nb; *Bc_out = Bc;
+    return MVUS_OK;
+}
+
+inline int solver_alloc(mvus_ba_ctx* h) {
+    int rc = solver_dims(h, h->world, &h->bw, &h->nb, &h->Bc);
+    if (rc) return rc;
+    h->q = 3 * h->bw;
     h->ncP = h->nc * h->Pc;
     h->ldw = h->ncP + 1;
     if (h->ncP > 1152) return fail(h, MVUS_ERR_UNSUPPORTED, "more than 1152 camera unknowns");
@@ -805,7 +813,7 @@ inline int accumulate(mvus_ba_ctx* h) {
         MV_CUDA(h, h->chunk_key2.alloc(nch));
         MV_CUDA(h, h->chunk_id.alloc(nch));
         MV_CUDA(h, h->chunk_perm.alloc(nch));
-        MV_CUDA(h, h->k2_queue.alloc(1));
+        MV_CUDA(h, h->k2_queue.alloc(4));
         size_t tb = 0;
         MV_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, h->chunk_key.p, h->chunk_key2.p, h->chunk_id.p,
                                                    h->chunk_perm.p, nch, 0, 32, h->st));
@@ -815,7 +823,10 @@ inline int accumulate(mvus_ba_ctx* h) {
                                                               h->chunk_key.p, h->chunk_id.p);
         MV_CUDA(h, cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tb, h->chunk_key.p, h->chunk_key2.p, h->chunk_id.p,
                                                    h->chunk_perm.p, nch, 0, 32, h->st));
-        MV_CUDA(h, cudaMemsetAsync(h->k2_queue.p, 0, sizeof(int), h->st));
+        {   // [0] work queue, [1] smallest, [2] largest block-of-four-spans any warp saw (the touched rows)
+            const int init[3] = {0, 0x7fffffff, -1};
+            MV_CUDA(h, cudaMemcpyAsync(h->k2_queue.p, init, sizeof(init), cudaMemcpyHostToDevice, h->st));
+        }
         h->launches += 3;
         const int64_t n_rows = (int64_t)(h->nb + 1) * h->q;
         if ((n_rows + 2 * K2_GUARD) * (int64_t)h->ldw >= ((int64_t)1 << 32))        // K2 flushes with 32-bit offsets
@@ -838,15 +849,20 @@ inline int accumulate(mvus_ba_ctx* h) {
             h->Hb.p + (size_t)K2_GUARD * K2_BAND, n_rows, h->q, h->D.p, h->E.p);
         h->launches += 2;
     }
-    if (h->M > 0 && (h->world <= 1 || h->rank == 0)) {      // parameter-only rows: counted once
+    if (h->M > 0) {      // parameter-only rows: every rank takes the rows whose first control point it owns
+        int64_t lo = 0, hi = h->nb;
+        if (h->world > 1) owner_range(h, h->rank, &lo, &hi);
+        const int64_t c_lo = h->rank == 0 ? -1 : lo * h->bw;
+        const int64_t c_hi = h->rank == h->world - 1 ? ((int64_t)1 << 40) : hi * h->bw;
         accumulate_motion_kernel<<<(int)((h->M + 127) / 128), 128, 0, h->st>>>(
-            h->r.p + 2 * h->N, h->mbase.p, h->mJ.p, h->M, h->bw, h->ldw, h->D.p, h->E.p, h->Wp());
+            h->r.p + 2 * h->N, h->mbase.p, h->mJ.p, h->M, h->bw, h->ldw, c_lo, c_hi, h->D.p, h->E.p, h->Wp());
         h->launches++;
     }
     MV_CUDA(h, cudaGetLastError());
     return MVUS_OK;
 }
 
+inline void owner_range(const mvus_ba_ctx* h, int r, int64_t* lo, int64_t* hi);
 inline int reduce_normal_equations(mvus_ba_ctx* h, bool full);   // ba_nccl.cuh
 inline void owner_range(const mvus_ba_ctx* h, int r, int64_t* lo, int64_t* hi);
 inline int nccl_bcast0(mvus_ba_ctx* h, double* buf, size_t count);
@@ -985,6 +1001,7 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
     double* bc = h->A.p + (size_t)h->nc * h->Pc * h->Pc;
     double* rhs = h->Sd.p + (size_t)ldw * ldw;
     int* fail_flag = h->flag.p + 1;
+    bool timed = false;
     MV_CUDA(h, cudaMemsetAsync(fail_flag, 0, sizeof(int), h->st));
     MV_CUDA(h, cudaMemsetAsync(h->Sd.p, 0, h->Sd.bytes(), h->st));
     if (h->world <= 1) {
@@ -1001,8 +1018,12 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
         } else {
             v.Worig = h->Wp();             // first touch of every block reads W~ directly: no 2|W~| copy pass
         }
+        cudaEventRecord(h->evs[0], h->st);
         std::vector<int64_t> levels = bcr_eliminate(h, v, nb, true, fail_flag);
+        cudaEventRecord(h->evs[1], h->st);
         launch_syrk(h, h->Ww.p, nbq, h->Sd.p);
+        cudaEventRecord(h->evs[2], h->st);
+        timed = true;
         form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
             h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->frozen.p, h->Sd.p, rhs);
         h->launches++;
@@ -1037,6 +1058,7 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
         MV_CUDA(h, cudaMemsetAsync(h->Ww.p + hi * wn, 0, wn * sizeof(double), h->st));
         BcrView lv{h->Dw.p + lo * qq, h->Ew.p + lo * qq, h->Ww.p + lo * wn, h->ZL.p + lo * qq, h->dlt_s.p + lo * q, nloc + 1};
         std::vector<int64_t> llev;
+        cudaEventRecord(h->evs[0], h->st);
         if (nloc > 0 && Bc > 1) {
             llev = bcr_eliminate(h, lv, Bc, false, fail_flag);
             launch_level(h, lv, (int)((lv.nb + Bc - 1) / Bc), Bc, Bc / 2, 2, fail_flag);     // pending updates of the last local level
@@ -1056,8 +1078,11 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
         BcrView tv{Dt, Et, Wt, h->ZLt.p, h->dst.p, nchunks};
         std::vector<int64_t> tlev = bcr_eliminate(h, tv, nchunks, true, fail_flag);
         // Schur complement: local rows (+ the replicated top rows once, on rank 0), summed over ranks
+        cudaEventRecord(h->evs[1], h->st);
         launch_syrk(h, h->Ww.p + lo * wn, nloc * q, h->Sd.p);
         if (h->rank == 0) launch_syrk(h, Wt, nchunks * q, h->Sd.p);
+        cudaEventRecord(h->evs[2], h->st);
+        timed = true;
         e = nccl_sum(h, h->Sd.p, (size_t)ldw * ldw);
         if (e) return e;
         form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
@@ -1086,6 +1111,12 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
     int f = 0;
     MV_CUDA(h, cudaMemcpyAsync(&f, fail_flag, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     MV_CUDA(h, cudaStreamSynchronize(h->st));
+    if (timed) {
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, h->evs[0], h->evs[1]);
+        cudaEventElapsedTime(&b, h->evs[1], h->evs[2]);
+        h->ms_bcr += a; h->ms_syrk += b;
+    }
     *ok = f ? 0 : 1;
     return MVUS_OK;
 }

@@ -62,7 +62,10 @@ extern "C" int mvus_ba_create(const mvus_ba_desc* desc, mvus_ba_handle* out) {
     h->n_other = (int64_t)h->nc * h->Pc;
     e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
     if (e == cudaSuccess)
+    {
         for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreate(&h->ev[k]);
+        for (int k = 0; k < 6 && e == cudaSuccess; ++k) e = cudaEventCreate(&h->evs[k]);
+    }
     if (e == cudaSuccess) { h->h_pin_n = 64; e = cudaMallocHost((void**)&h->h_pin, h->h_pin_n * sizeof(double)); }
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, desc->device);
     if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); delete h; return MVUS_ERR_CUDA; }
@@ -84,12 +87,13 @@ extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
     for (auto* b : {&h->row_off, &h->tile_start, &h->knot_off, &h->ctrl_off, &h->xoff, &h->lut_off}) b->release();
     for (auto* b : {&h->tile_cam, &h->tile_cnt, &h->ncoef, &h->deg, &h->lut_n, &h->lut, &h->tau_spl, &h->span,
                     &h->mbase, &h->flag, &h->frozen, &h->chunk_tile0, &h->chunk_nt, &h->chunk_key, &h->chunk_key2,
-                    &h->chunk_id, &h->chunk_perm, &h->k2_queue})
+                    &h->chunk_id, &h->chunk_perm, &h->k2_queue, &h->touch})
         b->release();
     h->tau_flag.release();
     h->sort_tmp.release();
     if (h->h_pin) cudaFreeHost(h->h_pin);
     for (int k = 0; k < 8; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
+    for (int k = 0; k < 6; ++k) if (h->evs[k]) cudaEventDestroy(h->evs[k]);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
 }
@@ -461,6 +465,7 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
     mvus_ba_stats st;
     memset(&st, 0, sizeof(st));
     h->launches = 0;
+    h->ms_syrk = h->ms_bcr = h->ms_reduce = h->ms_k2 = 0.0;
     const double ftol = h->desc.ftol, xtol = h->desc.xtol, gtol = h->desc.gtol;
     const int max_nfev = h->desc.max_nfev > 0 ? h->desc.max_nfev : 100 * (int)std::min<int64_t>(h->n, 1000);
     MV_CUDA(h, cudaEventRecord(h->ev[6], h->st));
@@ -506,8 +511,11 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
     while (st.nfev < max_nfev && status == 0) {
         if (need_accum) {
             PhaseTimer t(h, 2, &st.ms_accum);
+            cudaEventRecord(h->evs[3], h->st);
             rc = accumulate(h);
+            cudaEventRecord(h->evs[4], h->st);
             if (!rc) rc = reduce_normal_equations(h, false);
+            cudaEventRecord(h->evs[5], h->st);
             if (!rc) rc = compute_diag(h);
             if (!rc && h->desc.rs_bounds) {
                 active_rho_kernel<<<(h->ncP + 127) / 128, 128, 0, h->st>>>(
@@ -516,6 +524,12 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
             }
             t.stop();
             if (rc) return rc;
+            {
+                float a = 0.f, b = 0.f;
+                cudaEventElapsedTime(&a, h->evs[3], h->evs[4]);
+                cudaEventElapsedTime(&b, h->evs[4], h->evs[5]);
+                h->ms_k2 += a; h->ms_reduce += b;
+            }
             need_accum = false;
         }
         int ok = 0;
@@ -629,6 +643,7 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
     MV_CUDA(h, cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]));
     st.ms_total = ms;
     st.launches = h->launches;
+    st.ms_syrk = h->ms_syrk; st.ms_bcr = h->ms_bcr; st.ms_reduce = h->ms_reduce; st.ms_k2 = h->ms_k2;
     if (stats) *stats = st;
     return MVUS_OK;
 }

@@ -28,7 +28,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, name, out):
+def _worker(rank, world, port, name, out, mode='count'):
     import torch
     import torch.distributed as dist
     from oracle import ba_oracle
@@ -38,7 +38,9 @@ def _worker(rank, world, port, name, out):
     fl, truth, bakw = cases.make(name)
     # motion rows are parameter-only: rank 0 owns them (the library adds them on every rank and
     # the host divides; here the oracle-side bookkeeping keeps them on rank 0)
-    local = shard.shard_scene(fl, rank, world)
+    n_ctrl = sum(len(t[1][0]) for t in fl.spline['tck'])
+    bounds = None if mode == 'count' else [(n_ctrl * r) // world for r in range(world + 1)]
+    local = shard.shard_scene(fl, rank, world, bounds)
     kw = dict(bakw)
     if rank != 0:
         kw['motion_reg'] = False
@@ -57,12 +59,14 @@ def _worker(rank, world, port, name, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('name', ['rs_F_gap'])
-def test_sharded_normal_equations_sum_to_global(name, tmp_path):
+@pytest.mark.parametrize('name,mode', [('rs_F_gap', 'count'), ('rs_F_gap', 'span')])
+def test_sharded_normal_equations_sum_to_global(name, mode, tmp_path):
+    """`count`: every camera's track cut into equal counts; `span`: cut along the control-point
+    ranges the ranks own (what the multi-GPU bench uses, shard.shard_detections_by_span)."""
     import torch.multiprocessing as mp
     from oracle import ba_oracle
     out = str(tmp_path / 'sum.npz')
-    mp.spawn(_worker, args=(2, _free_port(), name, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), name, out, mode), nprocs=2, join=True)
     got = np.load(out)
     fl, truth, bakw = cases.make(name)
     prob = ba_oracle.Problem(fl, fl.numCam, **bakw)
@@ -83,6 +87,25 @@ def test_shard_scene_keeps_every_camera():
         assert (cat == fl.detections[i]).all()
         assert all(p.detections[i].shape[1] > 0 for p in parts)
     assert parts[0].spline['tck'][0][1][0] is fl.spline['tck'][0][1][0] or True
+
+
+def test_span_sharding_is_a_time_partition():
+    """Sharding by span: a partition of every camera's detections into contiguous time slices whose
+    spans respect the bounds (uncovered detections ride with the covered one before them)."""
+    fl, truth, bakw = cases.make('rs_F_gap')
+    n_ctrl = sum(len(t[1][0]) for t in fl.spline['tck'])
+    for world in (2, 3, 8):
+        bounds = [(n_ctrl * r) // world for r in range(world + 1)]
+        parts = [shard.shard_detections_by_span(fl, r, bounds) for r in range(world)]
+        for i in range(fl.numCam):
+            cat = np.concatenate([p[i] for p in parts], axis=1)
+            assert (cat == fl.detections[i]).all()              # contiguous slices in rank order = the track
+            g = shard.span_index(fl, i)
+            pos = 0
+            for r in range(world):
+                gi = g[pos:pos + parts[r][i].shape[1]]
+                pos += parts[r][i].shape[1]
+                assert ((gi < 0) | ((gi >= bounds[r]) & (gi < bounds[r + 1]))).all()
 
 
 def test_batch_partition_covers_every_problem_once():
