@@ -117,7 +117,8 @@ def error_cam(scene, cam_id, mode='dist', motion_prior=False, norm=False):
     fp = FlatProblem(s, 1)
     hd = _cabi.Handle(fp, device=DEVICE)
     try:
-        r, span, _, _, _ = hd.residual_jacobian(fp.x0)
+        r = hd.residual(fp.x0)                      # residual-only K1: 40 B per detection, no Jacobian
+        cov = hd.visibility(fp.x0)[0] > 0           # covered by a spline interval (util.py:103-106)
         dg = hd.detections_global(fp.x0)
     finally:
         hd.close()
@@ -128,7 +129,6 @@ def error_cam(scene, cam_id, mode='dist', motion_prior=False, norm=False):
     eu, ev = r[:N], r[N:2 * N]
     if mode == 'each':
         return np.concatenate((eu, ev))
-    cov = span >= 0
     # the reference concatenates interval by interval; detections are time-sorted so this is the same order
     if mode == 'dist':
         return np.sqrt(eu[cov] ** 2 + ev[cov] ** 2)

@@ -15,7 +15,7 @@ def nvcc_cmd(extra=()):
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     return [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
             '-shared', '-Xcompiler', '-fPIC', '-Xcompiler', '-Wno-unknown-pragmas', '--cudart', 'shared',
-            '-o', OUT, SRC, '-ldl'] + list(extra)
+            '-o', OUT, SRC, '-ldl', '-lpthread'] + list(extra)
 
 
 def build(force=False, verbose=False):

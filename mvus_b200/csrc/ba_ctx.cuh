@@ -45,9 +45,11 @@ struct DevBuf {
         if (e == cudaSuccess) n = count; else p = nullptr;
         return e;
     }
-    void release() {
+    // sync = false: the caller has already made sure that nothing on any stream still uses the memory
+    // (mvus_ba_destroy synchronises once instead of once per buffer)
+    void release(bool sync = true) {
         if (p) {
-            cudaDeviceSynchronize();                 // nothing on any stream may still use it
+            if (sync) cudaDeviceSynchronize();       // nothing on any stream may still use it
             cudaFreeAsync(p, cudaStreamPerThread);
         }
         p = nullptr; n = 0;

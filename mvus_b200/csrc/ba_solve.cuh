@@ -11,9 +11,13 @@
 // S = A - sum_k (L_k^-1 W_k)^T (L_k^-1 W_k) is formed by an FP64 SYRK and factorised densely.
 // tests/proto/bcr_proto.py is the NumPy model of exactly this sequence.
 //
-// Why direct and not PCG: the BA normal matrix has 7 exact gauge zeros and collective
-// time-warp modes ~1e-3 against a largest eigenvalue ~1e9 (measured) -- condition
-// 1e12, far outside what CG in FP64 resolves; LM needs accurate steps along those modes.
+// Why direct and not PCG (profiles/r2_pcg_experiment.txt, tests/proto/pcg_experiment.py): J^T J has 7
+// gauge zeros and weak time-warp modes (1e-3 .. 1 against a largest eigenvalue ~1e9); the Marquardt-
+// damped, Jacobi-scaled matrix the solver actually sees has condition ~6e4 at lambda = 1e-4, and
+// block-Jacobi PCG needs 100-300 iterations for a step accurate to 1e-3 -- it does converge, but at
+// config 4 an iteration is at least one pass over W~ (2.8 GB, 0.45 ms) and ~200 of them cost 5x the
+// exact solve (18 ms), which is cheap here because only nc*Pc <= 1152 unknowns survive the Schur
+// complement.
 #pragma once
 #include "ba_ctx.cuh"
 #include "ba_k2.cuh"

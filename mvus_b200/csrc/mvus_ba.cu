@@ -7,6 +7,9 @@
 #include <cstdio>
 #include <string>
 #include <vector>
+#include <thread>
+#include <mutex>
+#include <algorithm>
 
 #include "ba_ctx.cuh"
 #include "ba_kernels.cuh"
@@ -77,25 +80,100 @@ extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
     if (!h) return;
     cudaSetDevice(h->desc.device);
     nccl_destroy(h);
-    cudaStreamSynchronize(h->st);
+    cudaDeviceSynchronize();                          // once; the buffers are then released without further syncs
     for (auto* b : {&h->frame, &h->xr, &h->yr, &h->obs_u, &h->obs_v, &h->calib, &h->height, &h->int_a,
                     &h->int_b, &h->knots, &h->spanpoly, &h->span_t0, &h->lut_t0, &h->lut_invh, &h->tau,
                     &h->x, &h->x_trial, &h->camprep, &h->r, &h->J, &h->mJ, &h->partial, &h->A, &h->D, &h->E,
                     &h->W, &h->Dw, &h->Ew, &h->Ww, &h->ZL, &h->Sd, &h->dlt_c, &h->dlt_s, &h->diag_c,
                     &h->diag_s, &h->gvec, &h->xs, &h->scratch, &h->gt_out, &h->Dt, &h->ZLt, &h->dst, &h->bs, &h->Hb})
-        b->release();
-    for (auto* b : {&h->row_off, &h->tile_start, &h->knot_off, &h->ctrl_off, &h->xoff, &h->lut_off}) b->release();
+        b->release(false);
+    for (auto* b : {&h->row_off, &h->tile_start, &h->knot_off, &h->ctrl_off, &h->xoff, &h->lut_off}) b->release(false);
     for (auto* b : {&h->tile_cam, &h->tile_cnt, &h->ncoef, &h->deg, &h->lut_n, &h->lut, &h->tau_spl, &h->span,
                     &h->mbase, &h->flag, &h->frozen, &h->chunk_tile0, &h->chunk_nt, &h->chunk_key, &h->chunk_key2,
                     &h->chunk_id, &h->chunk_perm, &h->k2_queue, &h->touch})
-        b->release();
-    h->tau_flag.release();
-    h->sort_tmp.release();
+        b->release(false);
+    h->tau_flag.release(false);
+    h->sort_tmp.release(false);
     if (h->h_pin) cudaFreeHost(h->h_pin);
     for (int k = 0; k < 8; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     for (int k = 0; k < 6; ++k) if (h->evs[k]) cudaEventDestroy(h->evs[k]);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host -> device copy of the detections.  The caller's arrays are pageable NumPy memory: one
+// cudaMemcpyAsync stream moves them at ~9 GB/s (the driver stages through one bounce buffer), which
+// was 167 ms of a 0.77 s config-4 call.  Large uploads are therefore cut into 8 MB pieces and staged by
+// UP_THREADS host threads, each with its own stream and two page-locked buffers (allocated once per
+// process): memcpy into pinned memory in parallel, DMA out of it.
+struct UploadSeg { double* dst; const double* src; size_t bytes; };
+namespace {
+constexpr int UP_THREADS = 4;
+constexpr size_t UP_CHUNK = 8u << 20;
+struct UploadPool {
+    void* pin[UP_THREADS][2] = {};
+    cudaStream_t st[UP_THREADS] = {};
+    cudaEvent_t ev[UP_THREADS][2] = {};
+    int device = -1;
+    bool ok = false;
+    bool init(int dev) {
+        if (ok && device == dev) return true;
+        if (ok) return false;                             // one device per process (one process per GPU)
+        for (int t = 0; t < UP_THREADS; ++t) {
+            if (cudaStreamCreateWithFlags(&st[t], cudaStreamNonBlocking) != cudaSuccess) return false;
+            for (int k = 0; k < 2; ++k) {
+                if (cudaHostAlloc(&pin[t][k], UP_CHUNK, cudaHostAllocDefault) != cudaSuccess) return false;
+                if (cudaEventCreateWithFlags(&ev[t][k], cudaEventDisableTiming) != cudaSuccess) return false;
+            }
+        }
+        device = dev; ok = true;
+        return true;
+    }
+};
+UploadPool g_upload;
+std::mutex g_upload_mutex;
+}  // namespace
+
+static cudaError_t upload_segments(int device, const std::vector<UploadSeg>& segs, cudaStream_t st) {
+    size_t total = 0;
+    for (const auto& s : segs) total += s.bytes;
+    std::unique_lock<std::mutex> lock(g_upload_mutex, std::defer_lock);
+    const bool threaded = total >= (64u << 20) && lock.try_lock() && g_upload.init(device);
+    if (!threaded) {
+        cudaGetLastError();
+        for (const auto& s : segs) {
+            cudaError_t e = cudaMemcpyAsync(s.dst, s.src, s.bytes, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    // pieces of at most UP_CHUNK bytes, dealt round-robin to the threads
+    struct Piece { char* dst; const char* src; size_t bytes; };
+    std::vector<Piece> pieces;
+    for (const auto& s : segs)
+        for (size_t o = 0; o < s.bytes; o += UP_CHUNK)
+            pieces.push_back({(char*)s.dst + o, (const char*)s.src + o, std::min(UP_CHUNK, s.bytes - o)});
+    cudaError_t err[UP_THREADS];
+    std::vector<std::thread> th;
+    for (int t = 0; t < UP_THREADS; ++t)
+        th.emplace_back([&, t]() {
+            cudaError_t e = cudaSetDevice(device);
+            int k = 0;
+            for (size_t i = t; i < pieces.size() && e == cudaSuccess; i += UP_THREADS, k ^= 1) {
+                e = cudaEventSynchronize(g_upload.ev[t][k]);              // the DMA out of this buffer is done
+                if (e != cudaSuccess) break;
+                memcpy(g_upload.pin[t][k], pieces[i].src, pieces[i].bytes);
+                e = cudaMemcpyAsync(pieces[i].dst, g_upload.pin[t][k], pieces[i].bytes, cudaMemcpyHostToDevice, g_upload.st[t]);
+                if (e == cudaSuccess) e = cudaEventRecord(g_upload.ev[t][k], g_upload.st[t]);
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(g_upload.st[t]);
+            err[t] = e;
+        });
+    for (auto& t : th) t.join();
+    for (int t = 0; t < UP_THREADS; ++t)
+        if (err[t] != cudaSuccess) return err[t];
+    return cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -140,13 +218,17 @@ static int set_detections_core(mvus_ba_ctx* h, const int64_t* count, const doubl
     MV_CUDA(h, h->frame.alloc(na));
     MV_CUDA(h, h->xr.alloc(na));
     MV_CUDA(h, h->yr.alloc(na));
-    for (int i = 0; i < nc; ++i) {
-        if (count[i] == 0) continue;
-        if (!frame[i] || !x[i] || !y[i]) return fail(h, MVUS_ERR_ARG, "null detection arrays");
-        const size_t nb = (size_t)count[i] * sizeof(double);
-        MV_CUDA(h, cudaMemcpyAsync(h->frame.p + cam_ptr[i], frame[i], nb, cudaMemcpyHostToDevice, h->st));
-        MV_CUDA(h, cudaMemcpyAsync(h->xr.p + cam_ptr[i], x[i], nb, cudaMemcpyHostToDevice, h->st));
-        MV_CUDA(h, cudaMemcpyAsync(h->yr.p + cam_ptr[i], y[i], nb, cudaMemcpyHostToDevice, h->st));
+    {
+        std::vector<UploadSeg> segs;
+        for (int i = 0; i < nc; ++i) {
+            if (count[i] == 0) continue;
+            if (!frame[i] || !x[i] || !y[i]) return fail(h, MVUS_ERR_ARG, "null detection arrays");
+            const size_t nb = (size_t)count[i] * sizeof(double);
+            segs.push_back({h->frame.p + cam_ptr[i], frame[i], nb});
+            segs.push_back({h->xr.p + cam_ptr[i], x[i], nb});
+            segs.push_back({h->yr.p + cam_ptr[i], y[i], nb});
+        }
+        MV_CUDA(h, upload_segments(h->desc.device, segs, h->st));
     }
     MV_CUDA(h, upload(h->height, height, (size_t)nc, h->st));
     MV_CUDA(h, upload(h->calib, calib, (size_t)nc * 9, h->st));
