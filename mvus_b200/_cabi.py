@@ -102,6 +102,8 @@ class PinnedPool:
     MIN_BYTES = 16 << 20
 
     def __init__(self):
+        import threading
+        self.lock = threading.Lock()     # (batch.solve_scenes runs several BA calls from host threads)
         self.free = []          # (nbytes, ptr)
         self.total = 0
         self.new_bytes = 0      # bytes newly pinned (diagnostic)
@@ -114,11 +116,12 @@ class PinnedPool:
             return np.empty(int(n), dtype=dtype)
         lib = load()
         ptr = None
-        for k, (sz, p) in enumerate(self.free):
-            if nbytes <= sz <= 2 * nbytes + (1 << 20):
-                ptr, cap = p, sz
-                del self.free[k]
-                break
+        with self.lock:
+            for k, (sz, p) in enumerate(self.free):
+                if nbytes <= sz <= 2 * nbytes + (1 << 20):
+                    ptr, cap = p, sz
+                    del self.free[k]
+                    break
         if ptr is None:
             if self.total + nbytes > self.CAP_BYTES:
                 return np.empty(int(n), dtype=dtype)

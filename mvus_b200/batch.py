@@ -14,13 +14,25 @@ def my_problems(n_problems, rank, world):
     return list(range(rank, n_problems, world))
 
 
-def solve_many(scenes, numCam=None, rank=0, world=1, **ba_kw):
-    """Run Scene.BA on every scene this rank owns.  Returns {index: OptimizeResult}."""
-    out = {}
-    for p in my_problems(len(scenes), rank, world):
-        sc = scenes[p]
-        out[p] = sc.BA(numCam or sc.numCam, **ba_kw)
-    return out
+def solve_many(scenes, numCam=None, rank=0, world=1, threads=8, **ba_kw):
+    """Run Scene.BA on every scene this rank owns.  Returns {index: OptimizeResult}.
+
+    Every problem has its own handle = its own CUDA stream, and the ctypes calls release the GIL, so
+    `threads` host threads keep that many small problems in flight on the GPU at once: a 7 x 5000
+    problem occupies a few per cent of a B200 and its LM loop is latency-bound (host round trips for the
+    accept / reject scalars), which is what the concurrency hides."""
+    mine = my_problems(len(scenes), rank, world)
+    return solve_scenes({p: scenes[p] for p in mine}, numCam=numCam, threads=threads, **ba_kw)
+
+
+def solve_scenes(scenes, numCam=None, threads=8, **ba_kw):
+    """{index: scene} -> {index: OptimizeResult}, `threads` problems in flight."""
+    if threads <= 1 or len(scenes) <= 1:
+        return {p: sc.BA(numCam or sc.numCam, **ba_kw) for p, sc in scenes.items()}
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(threads, len(scenes))) as pool:
+        futs = {p: pool.submit(sc.BA, numCam or sc.numCam, **ba_kw) for p, sc in scenes.items()}
+        return {p: f.result() for p, f in futs.items()}
 
 
 def gather_costs(results, n_problems):

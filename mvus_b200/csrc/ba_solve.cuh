@@ -374,28 +374,38 @@ syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, 
 }
 
 // S~[n][0..n) = sum over rows of W~[row][n] * W~[row][0..n): the right-hand-side row of the Schur system.
-// One warp per slab of rows, lane -> columns lane + 32 k (coalesced), split-K reduced with FP64 RED.
-__global__ void __launch_bounds__(256)
+// One CTA per slab of rows; thread -> columns tid + 256 k (a row is read with unit stride by the CTA), four rows
+// in flight per thread; split-K reduced with FP64 RED.  HBM-bound: one pass over W~.
+constexpr int RHS_T = 256, RHS_NC = (1152 + RHS_T - 1) / RHS_T;
+__global__ void __launch_bounds__(RHS_T)
 wtw_rhs_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, double* __restrict__ Sfull) {
-    const int lane = threadIdx.x & 31;
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t r0 = w * slab, r1 = r0 + slab < R ? r0 + slab : R;
-    if (r0 >= R) return;
-    constexpr int NC = 1152 / 32;
-    double acc[NC];
+    const int64_t r0 = (int64_t)blockIdx.x * slab, r1 = r0 + slab < R ? r0 + slab : R;
+    double acc[RHS_NC];
 #pragma unroll
-    for (int k = 0; k < NC; ++k) acc[k] = 0.0;
-    for (int64_t row = r0; row < r1; ++row) {
-        const double* wr = Ww + row * ldw;
-        const double g = wr[n];
-        if (g == 0.0) continue;
+    for (int k = 0; k < RHS_NC; ++k) acc[k] = 0.0;
+    for (int64_t row = r0; row < r1; row += 4) {
+        double g[4], v[4][RHS_NC];
 #pragma unroll
-        for (int k = 0; k < NC; ++k)
-            if (lane + 32 * k < n) acc[k] += g * wr[lane + 32 * k];
+        for (int u = 0; u < 4; ++u) {
+            const bool in = row + u < r1;
+            const double* wr = Ww + (row + u) * ldw;
+            g[u] = in ? __ldg(wr + n) : 0.0;
+#pragma unroll
+            for (int k = 0; k < RHS_NC; ++k) {
+                const int c = threadIdx.x + RHS_T * k;
+                v[u][k] = (in && c < n) ? __ldcs(wr + c) : 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < RHS_NC; ++k) acc[k] += g[u] * v[u][k];
     }
 #pragma unroll
-    for (int k = 0; k < NC; ++k)
-        if (lane + 32 * k < n && acc[k] != 0.0) atomicAdd(Sfull + (int64_t)n * ldw + lane + 32 * k, acc[k]);
+    for (int k = 0; k < RHS_NC; ++k) {
+        const int c = threadIdx.x + RHS_T * k;
+        if (c < n && acc[k] != 0.0) atomicAdd(Sfull + (int64_t)n * ldw + c, acc[k]);
+    }
 }
 
 // rs_bounds (common.py:655-660, scipy trf_bounds): active-set treatment of the box 0 <= rho <= 1.
@@ -958,9 +968,8 @@ inline void launch_syrk(mvus_ba_ctx* h, const double* Wrows, int64_t R, double* 
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM); attr_set = true; }
     syrk_kernel<<<g, 512, SY_SMEM, h->st>>>(Wrows, R, ldw, n, slab, Sfull);
-    const int rslab = 64;                                  // rows per warp of the right-hand-side GEMV
-    const int64_t nwarps = (R + rslab - 1) / rslab;
-    wtw_rhs_kernel<<<(int)((nwarps * 32 + 255) / 256), 256, 0, h->st>>>(Wrows, R, ldw, n, rslab, Sfull);
+    const int rslab = 128;                                 // rows per CTA of the right-hand-side GEMV
+    wtw_rhs_kernel<<<(int)((R + rslab - 1) / rslab), RHS_T, 0, h->st>>>(Wrows, R, ldw, n, rslab, Sfull);
     h->launches += 2;
 }
 
