@@ -69,7 +69,7 @@ typedef struct mvus_ba_desc {
 typedef struct mvus_ba_stats {
     double  cost0;           /* 0.5*|r(x0)|^2                                             */
     double  cost;            /* 0.5*|r(x*)|^2                                             */
-    double  optimality;      /* |J^T r|_inf at x*                                         */
+    double  optimality;      /* |J^T r|_inf at the last point a Jacobian was evaluated at  */
     double  lambda;          /* final LM damping                                          */
     int32_t nfev;            /* residual evaluations                                      */
     int32_t njev;            /* Jacobian evaluations                                      */
@@ -158,6 +158,13 @@ int mvus_ba_detections_global(mvus_ba_handle h, const double* x, double* out);
  * util.py:103-106).  visible[N] int64, concatenated in camera order. */
 int mvus_ba_visibility(mvus_ba_handle h, const double* x, int64_t* visible);
 
+/* Device memory: handles allocate from a memory pool PRIVATE to this library (one per device; the
+ * process-wide default pool is not touched).  Destroyed handles leave their memory cached in that
+ * pool for the next handle (config 4 needs ~35 GB; main.py makes two BA calls per camera);
+ * mvus_ba_trim returns everything above keep_bytes to the driver.  The NCCL communicator
+ * (mvus_ba_comm_init) and the page-locked staging buffers live until the process exits. */
+int mvus_ba_trim(int32_t device, uint64_t keep_bytes);
+
 /* Page-locked host buffers for large outputs (device->host copies at PCIe speed). */
 void* mvus_ba_host_alloc(size_t bytes);
 void  mvus_ba_host_free(void* p);
@@ -188,6 +195,23 @@ int mvus_ba_spline_to_traj(mvus_ba_handle h, const double* x, const double* t, i
  * Any output may be NULL. */
 int mvus_ba_normal_equations(mvus_ba_handle h, const double* x, double* A, double* g,
                              double* Hss, int32_t* band_ctrl, double* Hcs, double* cost);
+
+/* ---- smoothing-spline fit (Scene.traj_to_spline, common.py:224-270; triangulate's refit :754-815) ----
+ * The per-data-point arithmetic of scipy.interpolate.splprep (FITPACK parcur/fppara) on the device; the
+ * knot-placement / smoothing-parameter decisions are host logic (mvus_b200/splfit.py).  A handle holds the
+ * data of ONE interval: u[m] ascending parameter values (time stamps), x[idim][m] row-major, degree k (1 or 3). */
+typedef struct mvus_spl_ctx* mvus_spl_handle;
+int mvus_ba_spl_create(int32_t device, int64_t m, int32_t idim, int32_t k, const double* u, const double* x,
+                       mvus_spl_handle* out);
+void mvus_ba_spl_destroy(mvus_spl_handle h);
+const char* mvus_ba_spl_last_error(mvus_spl_handle h);
+/* One solve on the knots t[n] (n >= 2k+2, k+1-fold end knots):  min sum |x_i - s(u_i)|^2 + pscale * c^T P c,
+ * P given by its upper band pen[(k+2)][n-k-1] (pen[d][j] = P[j-d][j]; NULL = plain least squares).
+ * Outputs, any may be NULL: c[idim][n-k-1] B-spline coefficients, fp = residual sum of squares,
+ * fpint[n-2k-1] = FITPACK's per-knot-interval residual sums (a point on an interior knot counts half on
+ * each side), diag_sum = sum of the diagonal of the triangular factor of the normal matrix. */
+int mvus_ba_spl_solve(mvus_spl_handle h, int32_t n, const double* t, const double* pen, double pscale,
+                      double* c, double* fp, double* fpint, double* diag_sum);
 
 /* Multi-GPU (one process per GPU): join an NCCL communicator whose unique id was
  * produced by mvus_ba_nccl_unique_id on rank 0 and broadcast by the host framework

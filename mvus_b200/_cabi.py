@@ -41,8 +41,9 @@ EXPORTS = ['mvus_ba_version', 'mvus_ba_create', 'mvus_ba_destroy', 'mvus_ba_last
            'mvus_ba_set_detections', 'mvus_ba_set_detections_rows', 'mvus_ba_set_splines', 'mvus_ba_dims', 'mvus_ba_residual',
            'mvus_ba_residual_jacobian', 'mvus_ba_solve', 'mvus_ba_detections_global',
            'mvus_ba_normal_equations', 'mvus_ba_global_traj', 'mvus_ba_spline_to_traj', 'mvus_ba_visibility', 'mvus_ba_host_alloc',
-           'mvus_ba_host_free', 'mvus_ba_nccl_unique_id', 'mvus_ba_comm_init', 'mvus_ba_shard_bounds',
-           'mvus_ba_time_resjac', 'mvus_ba_time_accumulate']
+           'mvus_ba_host_free', 'mvus_ba_trim', 'mvus_ba_nccl_unique_id', 'mvus_ba_comm_init', 'mvus_ba_shard_bounds',
+           'mvus_ba_time_resjac', 'mvus_ba_time_accumulate', 'mvus_ba_spl_create', 'mvus_ba_spl_destroy',
+           'mvus_ba_spl_last_error', 'mvus_ba_spl_solve']
 
 _lib = None
 
@@ -85,7 +86,15 @@ def load():
     lib.mvus_ba_host_free.restype = None
     lib.mvus_ba_nccl_unique_id.argtypes = [ctypes.c_char_p]
     lib.mvus_ba_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_char_p]
+    lib.mvus_ba_trim.argtypes = [ctypes.c_int32, ctypes.c_uint64]
     lib.mvus_ba_shard_bounds.argtypes = [ctypes.c_void_p, ctypes.c_int32, _lp]
+    lib.mvus_ba_spl_create.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _dp, _dp,
+                                       ctypes.POINTER(ctypes.c_void_p)]
+    lib.mvus_ba_spl_destroy.argtypes = [ctypes.c_void_p]
+    lib.mvus_ba_spl_destroy.restype = None
+    lib.mvus_ba_spl_last_error.argtypes = [ctypes.c_void_p]
+    lib.mvus_ba_spl_last_error.restype = ctypes.c_char_p
+    lib.mvus_ba_spl_solve.argtypes = [ctypes.c_void_p, ctypes.c_int32, _dp, _dp, ctypes.c_double, _dp, _dp, _dp, _dp]
     lib.mvus_ba_time_resjac.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int32, _dp]
     lib.mvus_ba_time_accumulate.argtypes = [ctypes.c_void_p, ctypes.c_int32, _dp]
     _lib = lib
@@ -304,3 +313,47 @@ class Handle:
         ms = ctypes.c_double()
         self._check(self.lib.mvus_ba_time_accumulate(self.h, reps, ctypes.byref(ms)))
         return ms.value
+
+
+class SplHandle:
+    """Data of one spline interval on the GPU (wraps mvus_spl_handle): u[m] ascending, x[idim][m]."""
+
+    def __init__(self, u, x, k=3, device=0):
+        self.lib = load()
+        self.u = np.ascontiguousarray(u, dtype=np.float64)
+        self.x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        self.k, self.idim, self.m = int(k), self.x.shape[0], len(self.u)
+        self.h = ctypes.c_void_p()
+        rc = self.lib.mvus_ba_spl_create(int(device), self.m, self.idim, self.k, _d(self.u), _d(self.x), ctypes.byref(self.h))
+        if rc != 0:
+            msg = self.lib.mvus_ba_spl_last_error(None).decode()
+            if rc == -1:
+                raise TypeError(msg)               # splprep raises TypeError('m > k must hold') here
+            raise MvusError('mvus_ba_spl_create: %s' % msg)
+
+    def solve(self, t, pen=None, pscale=0.0):
+        """-> (c [idim x (n-k-1)], fp, fpint [n-2k-1], diag_sum) on the knots t."""
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        n, k = len(t), self.k
+        c = np.empty((self.idim, n - k - 1))
+        fpint = np.empty(n - 2 * k - 1)
+        fp, ds = ctypes.c_double(), ctypes.c_double()
+        if pen is not None:
+            pen = np.ascontiguousarray(pen, dtype=np.float64)
+            assert pen.shape == (k + 2, n - k - 1)
+        rc = self.lib.mvus_ba_spl_solve(self.h, n, _d(t), _d(pen), float(pscale), _d(c), ctypes.byref(fp), _d(fpint),
+                                        ctypes.byref(ds))
+        if rc != 0:
+            raise MvusError('mvus_ba_spl_solve %d: %s' % (rc, self.lib.mvus_ba_spl_last_error(self.h).decode()))
+        return c, fp.value, fpint, ds.value
+
+    def close(self):
+        if self.h:
+            self.lib.mvus_ba_spl_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

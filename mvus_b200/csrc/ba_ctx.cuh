@@ -27,11 +27,14 @@ struct JBlk {
 __host__ __device__ __forceinline__ int jblk_off(int plane, int t) { return plane * 32 + (t ^ ((plane & 3) << 2)); }
 inline int jblk_doubles(int P) { return (2 * P + 2) * 32 + 16; }
 
-// Device buffer on the stream-ordered allocator.  The device's default memory pool is told to
-// keep freed memory (release threshold = max, set in mvus_ba_create), so the ~35 GB a config-4
-// handle needs are cudaMalloc'ed once per process and re-used by every later BA call (the
-// reference's main.py makes two BA calls per camera); plain cudaMalloc/cudaFree of that much memory
-// costs several hundred ms per call.
+// Device buffer on the stream-ordered allocator, from the library's OWN memory pool (one per device,
+// created by mvus_ba_create; the process-wide default pool, which torch or any other cudaMallocAsync
+// user shares, is left alone).  The pool keeps freed memory (release threshold = max), so the ~35 GB a
+// config-4 handle needs are obtained from the driver once per process and re-used by every later BA call
+// (the reference's main.py makes two BA calls per camera); plain cudaMalloc/cudaFree of that much memory
+// costs several hundred ms per call.  mvus_ba_trim() hands the cached memory back to the driver.
+cudaMemPool_t library_pool(int device);      // mvus_ba.cu
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -40,7 +43,11 @@ struct DevBuf {
         if (count <= n && p) return cudaSuccess;
         release();
         if (count == 0) return cudaSuccess;
-        cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), cudaStreamPerThread);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaMemPool_t pool = library_pool(dev);
+        cudaError_t e = pool ? cudaMallocFromPoolAsync((void**)&p, count * sizeof(T), pool, cudaStreamPerThread)
+                             : cudaMallocAsync((void**)&p, count * sizeof(T), cudaStreamPerThread);
         if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);   // usable on any stream afterwards
         if (e == cudaSuccess) n = count; else p = nullptr;
         return e;
@@ -117,6 +124,8 @@ struct mvus_ba_ctx {
     size_t w_guard = 0;                  // doubles in front of W~ inside the allocation W (K2's guard rows)
     double* Wp() const { return W.p ? W.p + w_guard : nullptr; }
     int launches = 0;
+    bool verbose = false;                // MVUS_BA_VERBOSE, read once at mvus_ba_create
+    double band_lo = 0.5, band_hi = 1.5; // trust-region band (MVUS_BA_BAND_LO / _HI at create: experiments only)
     int64_t cost_slot = 0;        // index in `partial` where the last evaluation left sum r^2
 
     // multi-GPU

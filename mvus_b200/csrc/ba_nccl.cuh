@@ -12,6 +12,7 @@
 #pragma once
 #include <dlfcn.h>
 #include <climits>
+#include <chrono>
 #include "ba_ctx.cuh"
 
 namespace mvus {
@@ -103,12 +104,17 @@ inline int reduce_normal_equations(mvus_ba_ctx* h, bool full) {
     }
     // ---- touched super-block range of every rank: [tlo, thi] (inclusive), empty if tlo > thi
     const int W = h->world;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
     std::vector<int> mine(2 * W, INT_MIN), all(2 * W, INT_MIN);
     {
         int kq[3] = {0, 0x7fffffff, -1};
         if (h->n_chunks > 0 && h->k2_queue.p)
             MV_CUDA(h, cudaMemcpyAsync(kq, h->k2_queue.p, sizeof(kq), cudaMemcpyDeviceToHost, h->st));
         MV_CUDA(h, cudaStreamSynchronize(h->st));
+        if (h->verbose) fprintf(stderr, "[mvus_ba] rank %d: K2 + camera all-reduce done after %.3f ms (host wait)\n", h->rank, ms_since(t_start));
         int64_t tlo = h->nb, thi = -1;
         if (kq[2] >= 0) {                                  // K2: control points 4 bmin - 3 .. 4 bmax + 3
             tlo = std::max<int64_t>(0, (4 * (int64_t)kq[1] - 3)) / h->bw;
@@ -134,23 +140,38 @@ inline int reduce_normal_equations(mvus_ba_ctx* h, bool full) {
         int64_t lo, hi;
         owner_range(h, s, &lo, &hi);
         if (s == W - 1) hi = h->nb;
-        int64_t hlo = hi, hhi = lo;                        // hull of foreign touched blocks inside [lo, hi)
+        // hulls of the foreign touched blocks inside [lo, hi): one from the ranks before s (they reach into the
+        // low end), one from the ranks after s (high end); merged if they meet
+        int64_t seg[2][2] = {{hi, lo}, {hi, lo}};
         for (int r = 0; r < W; ++r) {
             if (r == s) continue;
             const int64_t tlo = -(int64_t)all[2 * r], thi = all[2 * r + 1];
             if (tlo > thi) continue;
             const int64_t a = std::max(tlo, lo), b = std::min(thi + 1, hi);
-            if (a < b) { hlo = std::min(hlo, a); hhi = std::max(hhi, b); }
+            int64_t* g = seg[r < s ? 0 : 1];
+            if (a < b) { g[0] = std::min(g[0], a); g[1] = std::max(g[1], b); }
         }
-        if (hhi <= hlo) continue;
-        const size_t nblk = (size_t)(hhi - hlo);
-        moved += (int64_t)nblk;
-        e = api.Reduce(h->D.p + hlo * qq, h->D.p + hlo * qq, nblk * qq, NCCL_FLOAT64, NCCL_SUM, s, h->nccl_comm, h->st);
-        if (!e) e = api.Reduce(h->E.p + hlo * qq, h->E.p + hlo * qq, nblk * qq, NCCL_FLOAT64, NCCL_SUM, s, h->nccl_comm, h->st);
-        if (!e) e = api.Reduce(h->Wp() + hlo * wn, h->Wp() + hlo * wn, nblk * wn, NCCL_FLOAT64, NCCL_SUM, s, h->nccl_comm, h->st);
+        if (seg[0][0] < seg[0][1] && seg[1][0] < seg[1][1] && seg[1][0] <= seg[0][1]) {
+            seg[0][0] = std::min(seg[0][0], seg[1][0]); seg[0][1] = std::max(seg[0][1], seg[1][1]);
+            seg[1][0] = hi; seg[1][1] = lo;
+        }
+        for (int k = 0; k < 2 && e == 0; ++k) {
+            const int64_t hlo = seg[k][0], hhi = seg[k][1];
+            if (hhi <= hlo) continue;
+            const size_t nblk = (size_t)(hhi - hlo);
+            moved += (int64_t)nblk;
+            e = api.Reduce(h->D.p + hlo * qq, h->D.p + hlo * qq, nblk * qq, NCCL_FLOAT64, NCCL_SUM, s, h->nccl_comm, h->st);
+            if (!e) e = api.Reduce(h->E.p + hlo * qq, h->E.p + hlo * qq, nblk * qq, NCCL_FLOAT64, NCCL_SUM, s, h->nccl_comm, h->st);
+            if (!e) e = api.Reduce(h->Wp() + hlo * wn, h->Wp() + hlo * wn, nblk * wn, NCCL_FLOAT64, NCCL_SUM, s, h->nccl_comm, h->st);
+        }
     }
     const int e2 = api.GroupEnd();
     h->halo_blocks = moved;
+    if (h->verbose) {
+        cudaStreamSynchronize(h->st);
+        fprintf(stderr, "[mvus_ba] rank %d: halo exchange of %lld of %lld super-blocks done after %.3f ms; touched [%d, %d]\n",
+                h->rank, (long long)moved, (long long)h->nb, ms_since(t_start), -all[2 * h->rank], all[2 * h->rank + 1]);
+    }
     if (e || e2) return fail(h, MVUS_ERR_NCCL, "grouped ncclReduce of the normal equations failed");
     return MVUS_OK;
 }

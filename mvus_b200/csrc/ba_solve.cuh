@@ -901,6 +901,7 @@ inline int compute_diag(mvus_ba_ctx* h, bool full_everywhere = false) {
     if (n3 > 0) {
         MV_CUDA(h, cudaMemsetAsync(h->xs.p + 8, 0, sizeof(double), h->st));
         sum_kernel<<<(int)((n3 + 255) / 256), 256, 0, h->st>>>(h->diag_s.p, n3, h->xs.p + 8);
+        if (h->world > 1) { const int e = nccl_bcast0(h, h->xs.p + 8, 1); if (e) return e; }   // same floor on every rank
         floor_kernel<<<(int)((n3 + 255) / 256), 256, 0, h->st>>>(h->diag_s.p, n3, h->xs.p + 8, DIAG_FLOOR_FRAC);
         h->launches += 2;
     }

@@ -16,6 +16,7 @@
 #include "ba_solve.cuh"
 #include "ba_nccl.cuh"
 #include "ba_bookkeeping.cuh"
+#include "spl_fit.cuh"
 
 using namespace mvus;
 
@@ -25,6 +26,36 @@ static inline double __longlong_as_double_host(double bits_as_double) {
     // step_dots_kernel stores max|g| with an integer atomicMax on the bit pattern; the slot is
     // read back as a double holding those same bits, so this is the identity.
     return bits_as_double;
+}
+
+// The library's private stream-ordered memory pool (one per device): freed buffers stay cached for the next
+// handle, the process-wide default pool is not touched.
+cudaMemPool_t mvus::library_pool(int device) {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!pools[device]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        pools[device] = pool;
+    }
+    return pools[device];
+}
+
+// Hand the device memory cached by destroyed handles back to the driver (keeps `keep_bytes`).
+extern "C" int mvus_ba_trim(int32_t device, uint64_t keep_bytes) {
+    cudaMemPool_t pool = mvus::library_pool(device);
+    if (!pool) return MVUS_ERR_CUDA;
+    cudaDeviceSynchronize();
+    return cudaMemPoolTrimTo(pool, (size_t)keep_bytes) == cudaSuccess ? MVUS_OK : MVUS_ERR_CUDA;
 }
 
 extern "C" const char* mvus_ba_version(void) { return "mvus-b200 0.1 (sm_100a, fp64)"; }
@@ -48,15 +79,11 @@ extern "C" int mvus_ba_create(const mvus_ba_desc* desc, mvus_ba_handle* out) {
     if (desc->device < 0 || desc->device >= ndev) { g_create_err = "bad device ordinal"; return MVUS_ERR_ARG; }
     e = cudaSetDevice(desc->device);
     if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); return MVUS_ERR_CUDA; }
-    {   // keep freed device memory in the pool for the next handle (see DevBuf)
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, desc->device) == cudaSuccess) {
-            uint64_t thr = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-        cudaGetLastError();
-    }
+    if (!mvus::library_pool(desc->device)) cudaGetLastError();      // (falls back to the default pool)
     mvus_ba_ctx* h = new mvus_ba_ctx();
+    h->verbose = getenv("MVUS_BA_VERBOSE") != nullptr;              // diagnostics: read here, once, not inside the solve
+    if (getenv("MVUS_BA_BAND_LO")) h->band_lo = atof(getenv("MVUS_BA_BAND_LO"));
+    if (getenv("MVUS_BA_BAND_HI")) h->band_hi = atof(getenv("MVUS_BA_BAND_HI"));
     h->desc = *desc;
     h->nc = desc->num_cams;
     h->C = desc->opt_calib ? 15 : 6;
@@ -509,6 +536,10 @@ static int step_scalars(mvus_ba_ctx* h, const double* xd, double out[5]) {
                                                                   h->diag_s.p, bc, h->bs.p, h->ncP,
                                                                   3 * h->n_ctrl, xd, h->n, h->xs.p);
     h->launches++;
+    // multi-GPU: the sums come from atomics in a non-deterministic order; every rank must take the SAME
+    // accept / reject / lambda decisions (or the ranks would issue different numbers of collectives), so rank
+    // 0's values are the values
+    if (h->world > 1) { const int e = nccl_bcast0(h, h->xs.p, 5); if (e) return e; }
     MV_CUDA(h, cudaMemcpyAsync(h->h_pin, h->xs.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     MV_CUDA(h, cudaStreamSynchronize(h->st));
     for (int k = 0; k < 5; ++k) out[k] = h->h_pin[k];
@@ -571,9 +602,8 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
     // Delta to |delta|_D / 4, a very good one at the boundary doubles it.  Re-solving for a new
     // lambda costs linear solves but no residual evaluations (nfev is what max_iter caps).
     const double lam_min = 1e-10;
-    const bool verbose = getenv("MVUS_BA_VERBOSE") != nullptr;
-    const double band_lo = getenv("MVUS_BA_BAND_LO") ? atof(getenv("MVUS_BA_BAND_LO")) : 0.5;
-    const double band_hi = getenv("MVUS_BA_BAND_HI") ? atof(getenv("MVUS_BA_BAND_HI")) : 1.5;
+    const bool verbose = h->verbose;
+    const double band_lo = h->band_lo, band_hi = h->band_hi;
     double lam = 1e-4, Delta = -1.0;
     double pexp = 2.0 / 3.0;          // running estimate of p in |delta|_D ~ lambda^-p
     double last_l = -1.0, last_n = 0.0;
@@ -622,6 +652,7 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
         if (rc) return rc;
         if (ok && Delta < 0.0) Delta = nrm;
         double prev_l = ok ? lam : -1.0, prev_n = nrm;
+        double good_l = ok ? lam : -1.0;      // last lambda whose solve succeeded (dlt_* / sc belong to the LAST solve)
         // bracket / secant search on lambda (log scale) for |delta|_D ~ Delta
         double lo_l = -1, lo_n = 0, hi_l = -1, hi_n = 0;
         for (int its = 0; its < 10; ++its) {
@@ -639,8 +670,8 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
                 lam = std::sqrt(lo_l * hi_l);
             } else if (lo_l > 0) {
                 const double f = ok ? std::pow(nrm / Delta, 1.0 / pexp) : 10.0;
+                if (std::max(lam * f, lam * 2.0) > 1e30) break;      // (lam stays the one that was solved for)
                 lam = std::max(lam * f, lam * 2.0);
-                if (lam > 1e30) break;
             } else {
                 lam = std::max(std::min(lam * std::pow(nrm / Delta, 1.0 / pexp), lam * 0.5), lam_min);
             }
@@ -651,7 +682,12 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
                 const double pe = -std::log(nrm / prev_n) / std::log(lam / prev_l);
                 if (std::isfinite(pe)) pexp = std::min(std::max(pe, 0.15), 1.0);
             }
-            if (ok) { prev_l = lam; prev_n = nrm; }
+            if (ok) { prev_l = lam; prev_n = nrm; good_l = lam; }
+        }
+        if (!ok && good_l > 0.0) {            // the search ended on a failed factorisation: go back to the last good step
+            lam = good_l;
+            rc = solve_norm(lam, &ok, &nrm);
+            if (rc) return rc;
         }
         if (!ok) { status = -1; break; }
         last_l = lam; last_n = nrm;

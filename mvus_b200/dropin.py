@@ -1,6 +1,7 @@
 """Install the GPU bundle adjustment under the UNMODIFIED reference: replaces the methods of
-``reconstruction.common.Scene`` that sit on the BA path so that the reference's own
-``main.py`` runs with its inner loop on the B200.  See INTEGRATION.md."""
+``reconstruction.common.Scene`` that sit on the BA path (BA, error_cam, remove_outliers and the
+spline fit traj_to_spline either side of it) so that the reference's own ``main.py`` runs with
+its inner loop on the B200.  See INTEGRATION.md."""
 from . import ba
 
 
@@ -32,13 +33,17 @@ def install(common_module, satellites=True):
         Scene.remove_outliers = lambda self, cams, thres=30, verbose=False: ba.remove_outliers(
             self, cams, thres=thres, verbose=verbose)
         Scene._reference_error_cam, Scene._reference_remove_outliers = orig_err, orig_rm
+        # the spline (re)fit either side of every BA: init (main.py:36) and triangulate's refit (common.py:812)
+        from . import splfit
+        Scene._reference_traj_to_spline = Scene.traj_to_spline
+        Scene.traj_to_spline = lambda self, smooth_factor: splfit.traj_to_spline(self, smooth_factor)
     return original
 
 
 def uninstall(common_module):
     """Put the reference's own methods back."""
     Scene = common_module.Scene
-    for name in ('BA', 'error_cam', 'remove_outliers'):
+    for name in ('BA', 'error_cam', 'remove_outliers', 'traj_to_spline'):
         orig = Scene.__dict__.get('_reference_' + name)
         if orig is not None:
             setattr(Scene, name, orig)

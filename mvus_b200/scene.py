@@ -140,3 +140,7 @@ class Scene:
     def spline_to_traj(self, sampling_rate=1, t=None):
         from . import ba
         return ba.spline_to_traj(self, sampling_rate=sampling_rate, t=t)
+
+    def traj_to_spline(self, smooth_factor):
+        from . import splfit
+        return splfit.traj_to_spline(self, smooth_factor)

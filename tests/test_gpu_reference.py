@@ -236,3 +236,54 @@ def test_setters_after_a_solve_resize_the_solver(built_lib):
     assert st.nfev == st2.nfev and abs(st.cost - st2.cost) <= 1e-9 * st2.cost
     prob = ba_oracle.Problem(fl2, fl2.numCam, **bakw)
     assert abs(prob.cost(x) - st.cost) <= 1e-9 * st.cost
+
+
+# ---------------------------------------------------------------------------------------------
+# f2: the spline fit either side of every BA (Scene.traj_to_spline, common.py:224-270; triangulate's refit)
+SPL_CASES = [(300, 0.01, 1.0, 3, True), (300, 0.01, 0.5, 3, True), (2000, 0.02, 1.0, 3, True), (1500, 0.0, 6e-4, 3, False),
+             (500, 0.05, 4.0, 3, True), (500, 0.05, 4e8, 3, True), (64, 0.0, 0.0, 3, True), (400, 0.02, 3.0, 1, True),
+             (5, 0.0, 1e-6, 3, False), (20000, 0.01, 1.0, 3, True)]
+
+
+@pytest.mark.parametrize('case', SPL_CASES)
+def test_device_spline_fit_matches_splprep(case, built_lib):
+    """mvus_b200.splfit.splprep (CUDA solves + host knot strategy) against the installed
+    scipy.interpolate.splprep AND the oracle: identical knots, coefficients <= 1e-8 relative."""
+    from scipy import interpolate
+    from mvus_b200 import splfit
+    from oracle import fitpack_oracle as fo
+    m, noise, sf, k, jitter = case
+    rng = np.random.default_rng(0)
+    u = np.sort(rng.uniform(0, 600.0, m)) if jitter else np.linspace(0.0, 600.0, m)
+    x = synth.gt_trajectory(u) + rng.normal(size=(3, m)) * noise
+    s = sf * m * noise ** 2 if noise > 0 else sf
+    (tck, _), fp, ier, msg = interpolate.splprep(x, u=u, s=s, k=k, full_output=1)
+    t, c, fpd, ierd = splfit.fit(u, x, s, k)
+    assert len(t) == len(tck[0]) and np.array_equal(t, tck[0])
+    scale = max(np.abs(np.asarray(tck[1])).max(), 1.0)
+    assert max(np.abs(c[d] - tck[1][d]).max() for d in range(3)) <= 1e-8 * scale
+    assert ierd == ier and abs(fpd - fp) <= 1e-6 * max(fp, 1e-12) + 1e-18
+    if m <= 2000:
+        to, co, fpo, iero = fo.parcur_fit(u, x, s, k)
+        assert np.array_equal(t, to) and np.abs(c - co).max() <= 1e-8 * scale
+
+
+@needs_ref
+def test_traj_to_spline_on_device_matches_reference(built_lib):
+    """Scene.traj_to_spline on the device against the REFERENCE's own method on the same discrete
+    trajectory (several intervals, one too short for a cubic -> degree 1 fallback)."""
+    from mvus_b200.scene import Scene
+    common = ref_shim.load()
+    rng = np.random.default_rng(3)
+    tt = np.concatenate((np.arange(0.0, 400.0, 0.5), np.arange(420.0, 700.0, 0.5), np.arange(800.0, 806.0, 0.5)))
+    traj = np.vstack((tt, synth.gt_trajectory(tt) + rng.normal(size=(3, len(tt))) * 0.01))
+    ref, mine = common.Scene(), Scene()
+    ref.traj, mine.traj = traj.copy(), traj.copy()
+    ref.traj_to_spline(smooth_factor=[10, 20])
+    mine.traj_to_spline(smooth_factor=[10, 20])
+    assert np.array_equal(ref.spline['int'], mine.spline['int'])
+    assert len(ref.spline['tck']) == len(mine.spline['tck']) == 3
+    for a, b in zip(ref.spline['tck'], mine.spline['tck']):
+        assert a[2] == b[2] and np.array_equal(a[0], b[0])
+        for d in range(3):
+            assert np.abs(a[1][d] - b[1][d]).max() <= 1e-8 * max(1.0, np.abs(a[1][d]).max())
