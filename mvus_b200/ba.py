@@ -156,16 +156,16 @@ def remove_outliers(scene, cams, thres=30, verbose=False):
 
 def _spline_only_problem(scene):
     """A FlatProblem with the Scene's splines and one camera without detections: enough for the
-    entry points that only evaluate splines."""
+    entry points that only evaluate splines (also on a Scene that has no cameras yet)."""
     class _S:
         pass
     s = _S()
-    s.__dict__.update({k: getattr(scene, k) for k in ('settings', 'alpha', 'beta', 'rs', 'spline')})
-    s.cameras = scene.cameras
-    s.detections = list(scene.detections)
-    i0 = 0
-    s.detections[i0] = np.zeros((3, 0))
-    s.sequence = [i0]
+    s.spline = scene.spline
+    s.settings = {'opt_calib': False, 'undist_points': False}
+    s.alpha, s.beta, s.rs = np.ones(1), np.zeros(1), np.zeros(1)
+    cam = _S()
+    cam.K, cam.R, cam.t, cam.d, cam.resolution = np.eye(3), np.eye(3), np.zeros(3), np.zeros(5), [1, 1]
+    s.cameras, s.detections, s.sequence = [cam], [np.zeros((3, 0))], [0]
     return FlatProblem(s, 1)
 
 

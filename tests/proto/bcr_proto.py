@@ -104,6 +104,82 @@ def solve_bcr(A, bc, D, E, Wt, lam, dfloor=(1e-6, 1e32)):
     return dc, ds
 
 
+def prereduce(Dw, Ew, Ww, Lc):
+    """Chunk pre-reduction (ba_solve.cuh: chunk_factor_kernel / chunk_w_kernel): blocks are cut into chunks
+    of Lc; the first block of a chunk is its HEAD, the others are eliminated one after the other in ascending
+    order.  Eliminated block k keeps L_k, ZR_k (coupling to k+1, or to the next head for the last block of the
+    chunk) and ZH_k (fill-in coupling to its own head).  Returns the head system (Dt, Et, Wt) -- block
+    tridiagonal again, nchunk blocks -- and the factors (Lk, ZR, ZH, Ww with the eliminated rows W~_k)."""
+    nb, q, _ = Dw.shape
+    nch = (nb + Lc - 1) // Lc
+    Lk = np.zeros_like(Dw); ZR = np.zeros_like(Dw); ZH = np.zeros_like(Dw)
+    Wn = Ww.copy()
+    Dt = np.zeros((nch, q, q)); Et = np.zeros((nch, q, q)); Wt = np.zeros((nch,) + Ww.shape[1:])
+    DtR = np.zeros_like(Dt); G = np.zeros_like(Wt)          # contributions of the chunk on the LEFT
+    for c in range(nch):
+        j0, j1 = c * Lc, min(nb, (c + 1) * Lc)
+        Dh = Dw[j0].copy(); Wh = Ww[j0].copy()
+        if j1 - j0 == 1:                                     # head only: original coupling to the next head
+            Dt[c], Wt[c] = Dh, Wh
+            if j1 < nb:
+                Et[c] = Ew[j0]
+            Wn[j0] = 0.0
+            continue
+        F = Ew[j0].T.copy()                                  # rows j0+1, cols head
+        Dk = Dw[j0 + 1].copy(); wk = Ww[j0 + 1].copy()
+        for k in range(j0 + 1, j1):
+            Lk[k] = np.linalg.cholesky(Dk)
+            Er = Ew[k] if k + 1 < nb else np.zeros((q, q))   # rows k, cols k+1
+            ZR[k] = np.linalg.solve(Lk[k], Er)
+            ZH[k] = np.linalg.solve(Lk[k], F)
+            Wn[k] = np.linalg.solve(Lk[k], wk)
+            Dh -= ZH[k].T @ ZH[k]
+            Wh -= ZH[k].T @ Wn[k]
+            if k + 1 < j1:
+                Dk = Dw[k + 1] - ZR[k].T @ ZR[k]
+                wk = Ww[k + 1] - ZR[k].T @ Wn[k]
+                F = -ZR[k].T @ ZH[k]
+            elif k + 1 < nb:                                 # next head
+                DtR[c + 1] = ZR[k].T @ ZR[k]
+                G[c + 1] = ZR[k].T @ Wn[k]
+                Et[c] = -ZH[k].T @ ZR[k]                     # rows head c, cols head c+1
+        Dt[c], Wt[c] = Dh, Wh
+        Wn[j0] = 0.0                                         # head rows leave the eliminated set
+    Dt -= DtR
+    Wt -= G
+    return Dt, Et, Wt, Lk, ZR, ZH, Wn
+
+
+def solve_chunked(A, bc, D, E, Wt_in, lam, Lc, dfloor=(1e-6, 1e32)):
+    """Same system as solve_bcr, with the chunk pre-reduction in front of the cyclic reduction."""
+    nb, q, _ = D.shape
+    ncp = A.shape[0]
+    Dw = D.copy()
+    for k in range(nb):
+        Dw[k] += lam * np.diag(np.clip(np.diag(D[k]), *dfloor))
+    Dt, Et, Wt, Lk, ZR, ZH, Wn = prereduce(Dw, E, Wt_in, Lc)
+    # head system: cyclic reduction with lam = 0 on the already damped blocks.  The camera block must see the
+    # eliminated rows too: fold them into A, bc first (what the SYRK over all rows does on the device)
+    Sx = np.zeros((ncp + 1, ncp + 1))
+    for k in range(nb):
+        Sx += Wn[k].T @ Wn[k]
+    dA = np.clip(np.diag(A), *dfloor)
+    A2 = A + lam * np.diag(dA) - Sx[:ncp, :ncp]
+    bc2 = bc - Sx[:ncp, ncp]
+    dc, dst = solve_bcr(A2, bc2, Dt, Et, Wt, 0.0, dfloor=(0.0, 0.0))
+    ds = np.zeros((nb, q))
+    nch = Dt.shape[0]
+    for c in range(nch):
+        j0, j1 = c * Lc, min(nb, (c + 1) * Lc)
+        ds[j0] = dst[c]
+        for k in range(j1 - 1, j0, -1):
+            v = Wn[k][:, ncp] - Wn[k][:, :ncp] @ dc - ZH[k] @ ds[j0]
+            if k + 1 < nb:
+                v -= ZR[k] @ (ds[k + 1] if k + 1 < j1 else dst[c + 1])
+            ds[k] = np.linalg.solve(Lk[k].T, v)
+    return dc, ds
+
+
 if __name__ == '__main__':
     import sys
     sys.path.insert(0, '/root/repo')

@@ -287,3 +287,7 @@ def test_traj_to_spline_on_device_matches_reference(built_lib):
         assert a[2] == b[2] and np.array_equal(a[0], b[0])
         for d in range(3):
             assert np.abs(a[1][d] - b[1][d]).max() <= 1e-8 * max(1.0, np.abs(a[1][d]).max())
+    # and back: Scene.spline_to_traj on a Scene that has no cameras yet (main.py:36-37 order)
+    tr_ref, tr_mine = ref.spline_to_traj(), mine.spline_to_traj()
+    assert tr_ref.shape == tr_mine.shape and np.array_equal(tr_ref[0], tr_mine[0])
+    assert np.abs(tr_ref[1:] - tr_mine[1:]).max() <= 1e-7
