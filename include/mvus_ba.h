@@ -61,7 +61,8 @@ typedef struct mvus_ba_desc {
     int32_t device;          /* CUDA device ordinal                                       */
     double  motion_weight;   /* motion_weights (483-485)                                  */
     int32_t max_nfev;        /* max_iter -> least_squares(max_nfev=...) (670)             */
-    int32_t reserved0;
+    int32_t solver_chunk;    /* super-blocks per chunk of the pre-reduction in front of the cyclic reduction;
+                                0 = chosen from the problem size, 1 = cyclic reduction only */
     double  ftol, xtol, gtol;/* SciPy defaults 1e-8 / reference xtol=1e-12 / 1e-8 (670)   */
 } mvus_ba_desc;
 

@@ -19,7 +19,7 @@ class BADesc(ctypes.Structure):
                 ('opt_rs', ctypes.c_int32), ('rs_bounds', ctypes.c_int32),
                 ('motion_type', ctypes.c_int32), ('device', ctypes.c_int32),
                 ('motion_weight', ctypes.c_double), ('max_nfev', ctypes.c_int32),
-                ('reserved0', ctypes.c_int32), ('ftol', ctypes.c_double), ('xtol', ctypes.c_double),
+                ('solver_chunk', ctypes.c_int32), ('ftol', ctypes.c_double), ('xtol', ctypes.c_double),
                 ('gtol', ctypes.c_double)]
 
 
@@ -166,14 +166,14 @@ def _l(a):
 class Handle:
     """One BA problem on one GPU (wraps mvus_ba_handle)."""
 
-    def __init__(self, fp, device=0, ftol=1e-8, xtol=1e-12, gtol=1e-8, max_nfev=None):
+    def __init__(self, fp, device=0, ftol=1e-8, xtol=1e-12, gtol=1e-8, max_nfev=None, solver_chunk=0):
         self.lib = load()
         self.fp = fp
         desc = BADesc(num_cams=fp.nc, opt_calib=int(fp.opt_calib), undist_points=int(fp.undist),
                       opt_sync=int(fp.opt_sync), opt_rs=int(fp.opt_rs), rs_bounds=int(fp.rs_bounds),
                       motion_type=int(fp.motion_type), device=int(device),
                       motion_weight=float(fp.motion_weight),
-                      max_nfev=int(fp.max_nfev if max_nfev is None else max_nfev), reserved0=0,
+                      max_nfev=int(fp.max_nfev if max_nfev is None else max_nfev), solver_chunk=int(solver_chunk),
                       ftol=ftol, xtol=xtol, gtol=gtol)
         self.h = ctypes.c_void_p()
         rc = self.lib.mvus_ba_create(ctypes.byref(desc), ctypes.byref(self.h))

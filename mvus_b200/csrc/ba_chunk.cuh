@@ -28,8 +28,8 @@ namespace mvus {
 template <int Q>
 __global__ void __launch_bounds__(32)
 chunk_factor_kernel(int64_t nb, int Lc, int64_t c_first, double* __restrict__ Dw, double* __restrict__ Ew,
-                    double* __restrict__ ZL, double* __restrict__ Dh, double* __restrict__ Eh,
-                    double* __restrict__ DhR, int* __restrict__ fail_flag) {
+                    double* __restrict__ ZL, double* __restrict__ Linv, double* __restrict__ Dh,
+                    double* __restrict__ Eh, double* __restrict__ DhR, int* __restrict__ fail_flag) {
     constexpr int QQ = Q * Q;
     __shared__ double Dk[QQ], F[QQ], R[QQ], Hd[QQ], T1[QQ], T2[QQ];
     const int lane = threadIdx.x;
@@ -103,6 +103,7 @@ chunk_factor_kernel(int64_t nb, int Lc, int64_t c_first, double* __restrict__ Dw
             Dw[k * QQ + i] = Dk[i];
             Ew[k * QQ + i] = R[i];
             ZL[k * QQ + i] = F[i];
+            if (a == b) Linv[k * Q + a] = 1.0 / Dk[i];
         }
         __syncwarp();
         if (more) {
@@ -123,15 +124,24 @@ chunk_factor_kernel(int64_t nb, int Lc, int64_t c_first, double* __restrict__ Dw
 // grid (chunks, column groups of CW_T), block CW_T.  Wsrc: where a block's original rows are read (may be Ww
 // itself: every element is read before the same thread overwrites it).  Writes W~_k into Ww (zero rows for
 // the head), the head's rows into Wh[c] and the contribution to the NEXT head into Gh[c+1].
+// Per block k the CTA stages [L_k | ZH_k | ZR_k | 1/diag L_k] in shared memory (cp.async, double-buffered: the
+// matrices of block k+1 arrive while block k is computed; every thread reads them as broadcasts) and each
+// thread keeps three q-vectors: w (this block's rows of its column), wnx (the next block's rows, prefetched
+// one block ahead and already carrying -ZR_k^T W~_k when its turn comes) and wh (the head's accumulator).
 constexpr int CW_T = 128;
+__device__ __forceinline__ void cw_cp8(double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
 template <int Q>
-__global__ void __launch_bounds__(CW_T)
+__global__ void __launch_bounds__(CW_T, 4)
 chunk_w_kernel(int64_t nb, int Lc, int64_t c_first, int ldw, const double* __restrict__ Wsrc,
                const double* __restrict__ Dw, const double* __restrict__ Ew, const double* __restrict__ ZL,
-               double* __restrict__ Ww, double* __restrict__ Wh, double* __restrict__ Gh) {
+               const double* __restrict__ Linv, double* __restrict__ Ww, double* __restrict__ Wh,
+               double* __restrict__ Gh) {
     constexpr int QQ = Q * Q;
-    constexpr int NPF = (3 * QQ + CW_T - 1) / CW_T;       // matrix doubles each thread prefetches per block
-    __shared__ __align__(16) double sm[2][3 * QQ];        // [stage][L (diagonal inverted) | ZH | ZR of the previous block]
+    constexpr int NM = 3 * QQ + Q;                        // doubles per stage
+    constexpr int NMP = (NM + 1) & ~1;
+    __shared__ __align__(16) double sm[2][NMP];           // [stage][L | ZH | ZR | 1/diag]
     const int tid = threadIdx.x;
     const int64_t c = c_first + blockIdx.x;
     const int64_t j0 = c * Lc, j1 = (j0 + Lc < nb) ? j0 + Lc : nb;
@@ -140,52 +150,47 @@ chunk_w_kernel(int64_t nb, int Lc, int64_t c_first, int ldw, const double* __res
     const bool act = col < ldw;
     const int64_t wn = (int64_t)Q * ldw;
     const int cl = act ? col : 0;
-    double wh[Q], wp[Q], w[Q], wnx[Q];
+    double wh[Q], w[Q], wnx[Q];
 #pragma unroll
-    for (int a = 0; a < Q; ++a) { wh[a] = Wsrc[j0 * wn + (int64_t)a * ldw + cl]; wp[a] = 0.0; }
+    for (int a = 0; a < Q; ++a) { wh[a] = Wsrc[j0 * wn + (int64_t)a * ldw + cl]; wnx[a] = 0.0; }
     if (j1 - j0 > 1) {
-        // matrices of block k into stage st: element e of [L_k | ZH_k | ZR_{k-1}]
-        auto mat_src = [&](int64_t k, int e) -> double {
-            const int which = e / QQ, i = e - which * QQ;
-            if (which == 0) {
-                const double v = Dw[k * QQ + i];
-                return (i / Q == i % Q) ? 1.0 / v : v;
+        auto stage_mats = [&](int64_t k, int st) {
+            for (int e = tid; e < NM; e += CW_T) {
+                const double* src = e < QQ ? Dw + k * QQ + e : e < 2 * QQ ? ZL + k * QQ + (e - QQ)
+                                  : e < 3 * QQ ? Ew + k * QQ + (e - 2 * QQ) : Linv + k * Q + (e - 3 * QQ);
+                cw_cp8(&sm[st][e], src);
             }
-            if (which == 1) return ZL[k * QQ + i];
-            return k - 1 > j0 ? Ew[(k - 1) * QQ + i] : 0.0;
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        double pf[NPF];
-#pragma unroll
-        for (int u = 0; u < NPF; ++u) { const int e = tid + u * CW_T; if (e < 3 * QQ) sm[0][e] = mat_src(j0 + 1, e); }
+        stage_mats(j0 + 1, 0);
 #pragma unroll
         for (int a = 0; a < Q; ++a) wnx[a] = Wsrc[(j0 + 1) * wn + (int64_t)a * ldw + cl];
-        __syncthreads();
         for (int64_t k = j0 + 1; k < j1; ++k) {
             const int st = (int)((k - j0 - 1) & 1);
             const bool more = k + 1 < j1;
 #pragma unroll
-            for (int a = 0; a < Q; ++a) w[a] = wnx[a];
+            for (int a = 0; a < Q; ++a) { w[a] = wnx[a]; wnx[a] = 0.0; }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                              // block k's matrices are there; stage st^1 is free again
             if (more) {
-#pragma unroll
-                for (int u = 0; u < NPF; ++u) { const int e = tid + u * CW_T; if (e < 3 * QQ) pf[u] = mat_src(k + 1, e); }
+                stage_mats(k + 1, st ^ 1);
 #pragma unroll
                 for (int a = 0; a < Q; ++a) wnx[a] = Wsrc[(k + 1) * wn + (int64_t)a * ldw + cl];
             }
             const double* Lm = sm[st];
             const double* Zh = sm[st] + QQ;
             const double* Zr = sm[st] + 2 * QQ;
-#pragma unroll
-            for (int b = 0; b < Q; ++b) {
-                const double x = wp[b];
-#pragma unroll
-                for (int a = 0; a < Q; ++a) w[a] -= Zr[b * Q + a] * x;
-            }
+            const double* Li = sm[st] + 3 * QQ;
 #pragma unroll
             for (int i = 0; i < Q; ++i) {
                 double v = w[i];
 #pragma unroll
                 for (int kk = 0; kk < i; ++kk) v -= Lm[i * Q + kk] * w[kk];
-                w[i] = v * Lm[i * Q + i];
+                w[i] = v * Li[i];
+            }
+            if (act) {
+#pragma unroll
+                for (int a = 0; a < Q; ++a) Ww[k * wn + (int64_t)a * ldw + col] = w[a];
             }
 #pragma unroll
             for (int b = 0; b < Q; ++b) {
@@ -193,17 +198,13 @@ chunk_w_kernel(int64_t nb, int Lc, int64_t c_first, int ldw, const double* __res
 #pragma unroll
                 for (int a = 0; a < Q; ++a) wh[a] -= Zh[b * Q + a] * x;
             }
-            if (act) {
+            // -ZR_k^T W~_k goes to the next block's rows (or, after the last block, to the next head)
 #pragma unroll
-                for (int a = 0; a < Q; ++a) Ww[k * wn + (int64_t)a * ldw + col] = w[a];
+            for (int b = 0; b < Q; ++b) {
+                const double x = w[b];
+#pragma unroll
+                for (int a = 0; a < Q; ++a) wnx[a] -= Zr[b * Q + a] * x;
             }
-#pragma unroll
-            for (int a = 0; a < Q; ++a) wp[a] = w[a];
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < NPF; ++u) { const int e = tid + u * CW_T; if (e < 3 * QQ) sm[st ^ 1][e] = pf[u]; }
-            }
-            __syncthreads();
         }
     }
     if (!act) return;
@@ -213,17 +214,9 @@ chunk_w_kernel(int64_t nb, int Lc, int64_t c_first, int ldw, const double* __res
         Ww[j0 * wn + (int64_t)a * ldw + col] = 0.0;
     }
     if (j1 < nb) {
-        // contribution to the next head: ZR_last^T W~_last (zero if this chunk is a lone head: wp = 0 there,
-        // its coupling stays in E^h)
-        const double* Zr = Ew + (j1 - 1) * QQ;
-#pragma unroll 1
-        for (int a = 0; a < Q; ++a) {
-            double g = 0.0;
-            if (j1 - j0 > 1)
+        // contribution to the next head: ZR_last^T W~_last = -wnx (zero for a lone head, whose coupling stays in E^h)
 #pragma unroll
-                for (int b = 0; b < Q; ++b) g += Zr[b * Q + a] * wp[b];
-            Gh[(c + 1) * wn + (int64_t)a * ldw + col] = g;
-        }
+        for (int a = 0; a < Q; ++a) Gh[(c + 1) * wn + (int64_t)a * ldw + col] = (j1 - j0 > 1) ? -wnx[a] : 0.0;
     }
 }
 

@@ -121,6 +121,10 @@ struct mvus_ba_ctx {
     mvus::DevBuf<double> bs;             // spline right-hand side (-J^T r) as a contiguous vector
     mvus::DevBuf<double> Dt, ZLt, dst;   // top-level system of the sharded solve
     int64_t Bc = 1;                      // chunk size (super-blocks) of the sharded solve
+    // chunk pre-reduction (ba_chunk.cuh): Lc super-blocks per chunk, nh = ceil(nb / Lc) heads (+1 ghost)
+    int Lc = 1, Lc_req = 0;              // Lc_req: desc.solver_chunk (0 = choose from nb)
+    int64_t nh = 0;
+    mvus::DevBuf<double> Dh, Eh, Wh, ZLh, dsh, DhR, Gh, Linv;
     size_t w_guard = 0;                  // doubles in front of W~ inside the allocation W (K2's guard rows)
     double* Wp() const { return W.p ? W.p + w_guard : nullptr; }
     int launches = 0;

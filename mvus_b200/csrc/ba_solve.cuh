@@ -320,45 +320,70 @@ syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, 
     // diagonal tile pair contribute nothing: they still help staging, but skip the MMAs
     const bool warp_active = (ti * SY_T + wy * 32 < n) && (tj * SY_T + wx * 32 < n) && !(diag && wx > wy);
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(sy_smem);
-    // each thread stages 4 elements of each panel per chunk: idx = tid + 512*k -> (row kk, column cc)
+    // Staging: each thread copies 4 elements of each panel per chunk -- column cc = tid & 127 of the rows
+    // kq, kq + 4, kq + 8, kq + 12 (kq = tid >> 7).  Everything that does not change from chunk to chunk is
+    // computed once (the generic form cost ~220 instructions per warp and chunk, issued right after the
+    // barrier while the FP64-MMA pipe ran dry: profiles/r2_notes.md): two running row pointers, three row
+    // offsets, the per-thread zero-fill sizes of padding columns.
+    constexpr unsigned STAGE_B = 2u * SY_K * SY_LD * 8u, PANEL_B = SY_K * SY_LD * 8u, ROW4_B = 4u * SY_LD * 8u;
+    const int cc = tid & 127, kq = tid >> 7;
+    const bool cola = ti * SY_T + cc < n, colb = tj * SY_T + cc < n;
+    const unsigned sza = cola ? 8u : 0u, szb = colb ? 8u : 0u;
+    const double* pa = Ww + (r0 + kq) * ldw + (cola ? ti * SY_T + cc : 0);
+    const double* pb = Ww + (r0 + kq) * ldw + (colb ? tj * SY_T + cc : 0);
+    const unsigned soff = (unsigned)(kq * SY_LD + cc) * 8u;
+    const int64_t ld4 = 4 * (int64_t)ldw, ld16 = 16 * (int64_t)ldw;
+    const int nfull = (int)((r1 - r0) / SY_K);             // chunks whose 16 rows all exist
     auto issue = [&](int c) {
-        const int st = c % SY_STAGES;
-        const unsigned sa = sbase + (unsigned)(st * 2 * SY_K * SY_LD) * 8u, sb = sa + (unsigned)(SY_K * SY_LD) * 8u;
+        if (c < nchunk) {
+            const unsigned sa = sbase + (unsigned)(c % SY_STAGES) * STAGE_B + soff;
+            if (c < nfull) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int idx = tid + k * 512;
-            const int kk = idx >> 7, cc = idx & 127;
-            const int64_t row = r0 + (int64_t)c * SY_K + kk;
-            const bool inr = c < nchunk && row < r1;
-            const int ca = ti * SY_T + cc, cb = tj * SY_T + cc;
-            const unsigned off = (unsigned)(kk * SY_LD + cc) * 8u;
-            sy_cp8(sa + off, inr && ca < n ? Ww + row * ldw + ca : Ww, inr && ca < n);
-            if (!diag) sy_cp8(sb + off, inr && cb < n ? Ww + row * ldw + cb : Ww, inr && cb < n);
+                for (int k = 0; k < 4; ++k) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa + k * ROW4_B), "l"(pa + k * ld4), "r"(sza) : "memory");
+                    if (!diag)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa + PANEL_B + k * ROW4_B), "l"(pb + k * ld4), "r"(szb) : "memory");
+                }
+            } else {                                       // last, partial chunk of the slab: rows past r1 are zero-filled
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool inr = r0 + (int64_t)c * SY_K + kq + 4 * k < r1;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa + k * ROW4_B), "l"(inr ? pa + k * ld4 : Ww), "r"(inr ? sza : 0u) : "memory");
+                    if (!diag)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa + PANEL_B + k * ROW4_B), "l"(inr ? pb + k * ld4 : Ww), "r"(inr ? szb : 0u) : "memory");
+                }
+            }
+            pa += ld16; pb += ld16;
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto mma_step = [&](const double* As, const double* Bp, int ks) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i] = As[(ks + fk) * SY_LD + wy * 32 + i * 8 + fm];
+            b[i] = Bp[(ks + fk) * SY_LD + wx * 32 + i * 8 + fm];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     };
 #pragma unroll
     for (int c = 0; c < SY_STAGES - 1; ++c) issue(c);
     for (int c = 0; c < nchunk; ++c) {
         asm volatile("cp.async.wait_group %0;" :: "n"(SY_STAGES - 2) : "memory");
         __syncthreads();                       // chunk c has landed for everybody; stage (c - 1) % STAGES is free
-        issue(c + SY_STAGES - 1);
         const double* As = sy_smem + (size_t)(c % SY_STAGES) * 2 * SY_K * SY_LD;
         const double* Bp = diag ? As : As + SY_K * SY_LD;
-        if (warp_active)
+        // the first quarter of the chunk's MMAs is queued BEFORE the copies of chunk c + 3 are issued, so the
+        // FP64-MMA pipe has work while the warps of this scheduler run through their staging instructions
+        if (warp_active) mma_step(As, Bp, 0);
+        issue(c + SY_STAGES - 1);
+        if (warp_active) {
 #pragma unroll
-            for (int ks = 0; ks < SY_K; ks += 4) {
-                double a[4], b[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    a[i] = As[(ks + fk) * SY_LD + wy * 32 + i * 8 + fm];
-                    b[i] = Bp[(ks + fk) * SY_LD + wx * 32 + i * 8 + fm];
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-            }
+            for (int ks = 4; ks < SY_K; ks += 4) mma_step(As, Bp, ks);
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -793,6 +818,28 @@ inline int solver_alloc(mvus_ba_ctx* h) {
     MV_CUDA(h, h->Ew.alloc(nba * qq));
     MV_CUDA(h, h->Ww.alloc(nba * h->q * h->ldw));
     MV_CUDA(h, h->ZL.alloc(nba * qq));
+    // chunk pre-reduction (ba_chunk.cuh): long systems only -- below a few hundred super-blocks the cyclic
+    // reduction's handful of tiny launches is cheaper than a sequential sweep over a chunk
+    int Lc = h->Lc_req > 0 ? h->Lc_req : (h->nb >= 4096 ? 32 : h->nb >= 1024 ? 16 : h->nb >= 256 ? 8 : 1);
+    if (h->world > 1) {                                        // rank ranges are multiples of Bc (a power of two)
+        int p2 = 1;
+        while (p2 * 2 <= Lc && p2 * 2 <= h->Bc) p2 *= 2;
+        Lc = p2;
+    }
+    if (Lc >= h->nb) Lc = 1;
+    h->Lc = Lc;
+    h->nh = (h->nb + Lc - 1) / Lc;
+    if (Lc > 1) {
+        const size_t nha = (size_t)h->nh + 1;                  // +1: ghost head of the sharded solve
+        MV_CUDA(h, h->Dh.alloc(nha * qq));
+        MV_CUDA(h, h->Eh.alloc(nha * qq));
+        MV_CUDA(h, h->ZLh.alloc(nha * qq));
+        MV_CUDA(h, h->DhR.alloc(nha * qq));
+        MV_CUDA(h, h->Wh.alloc(nha * h->q * h->ldw));
+        MV_CUDA(h, h->Gh.alloc(nha * h->q * h->ldw));
+        MV_CUDA(h, h->dsh.alloc(nha * h->q));
+        MV_CUDA(h, h->Linv.alloc(nba * h->q));
+    }
     if (h->world > 1) {
         const size_t nch = (size_t)(h->nb / h->Bc);
         MV_CUDA(h, h->Dt.alloc(nch * (2 * qq + (size_t)h->q * h->ldw)));
@@ -1005,10 +1052,67 @@ __global__ void zero_outside_kernel(double* __restrict__ v, int64_t n, int64_t l
     if (i < n && (i < lo || i >= hi)) v[i] = 0.0;
 }
 
+// Chunk pre-reduction of the super-blocks [lo, hi) (multiples of Lc, or hi = nb): L/ZR/ZH of the eliminated
+// blocks into Dw/Ew/ZL, their W~ rows into Ww, the head system of chunks [lo/Lc, ceil(hi/Lc)) into Dh/Eh/Wh.
+// The head after the range (a ghost when another rank owns it) receives the last chunk's contribution.
+inline void prereduce_range(mvus_ba_ctx* h, int64_t lo, int64_t hi, const double* wsrc, int* fail_flag) {
+    const int Lc = h->Lc, q = h->q, ldw = h->ldw;
+    const size_t qq = (size_t)q * q;
+    const int64_t wn = (int64_t)q * ldw;
+    const int64_t c0 = lo / Lc, c1 = (hi + Lc - 1) / Lc;
+    if (c1 <= c0) return;
+    const bool has_next = hi < h->nb || h->world > 1;           // a head (or ghost slot) exists after the range
+    // the first head has no chunk on its left inside the range; the ghost starts from zero
+    cudaMemsetAsync(h->DhR.p + c0 * qq, 0, qq * sizeof(double), h->st);
+    cudaMemsetAsync(h->Gh.p + c0 * wn, 0, wn * sizeof(double), h->st);
+    if (has_next) {
+        cudaMemsetAsync(h->Dh.p + c1 * qq, 0, qq * sizeof(double), h->st);
+        cudaMemsetAsync(h->Eh.p + c1 * qq, 0, qq * sizeof(double), h->st);
+        cudaMemsetAsync(h->Wh.p + c1 * wn, 0, wn * sizeof(double), h->st);
+        if (hi >= h->nb) {                                      // last rank: nothing flows into the ghost
+            cudaMemsetAsync(h->DhR.p + c1 * qq, 0, qq * sizeof(double), h->st);
+            cudaMemsetAsync(h->Gh.p + c1 * wn, 0, wn * sizeof(double), h->st);
+        }
+    }
+    const int nchunk = (int)(c1 - c0);
+    // the kernels see the blocks [0, nbv): a block couples to its right neighbour iff that neighbour exists
+    const int64_t nbv = (hi < h->nb) ? hi + 1 : h->nb;
+    const dim3 gw(nchunk, (ldw + CW_T - 1) / CW_T);
+#define MV_CHUNK(QQ)                                                                                              \
+    chunk_factor_kernel<QQ><<<nchunk, 32, 0, h->st>>>(nbv, Lc, c0, h->Dw.p, h->Ew.p, h->ZL.p, h->Linv.p, h->Dh.p, h->Eh.p, \
+                                                      h->DhR.p, fail_flag);                                       \
+    chunk_w_kernel<QQ><<<gw, CW_T, 0, h->st>>>(nbv, Lc, c0, ldw, wsrc, h->Dw.p, h->Ew.p, h->ZL.p, h->Linv.p, h->Ww.p, h->Wh.p, h->Gh.p)
+    switch (q) {
+        case 9: MV_CHUNK(9); break;
+        case 12: MV_CHUNK(12); break;
+        case 15: MV_CHUNK(15); break;
+        default: MV_CHUNK(18); break;
+    }
+#undef MV_CHUNK
+    head_fix_kernel<<<(int)(c1 - c0 + (has_next ? 1 : 0)), 256, 0, h->st>>>(c0, q, ldw, h->Dh.p, h->DhR.p, h->Wh.p, h->Gh.p);
+    h->launches += 3;
+}
+
+inline void chunk_back_range(mvus_ba_ctx* h, int64_t lo, int64_t hi) {
+    const int Lc = h->Lc;
+    const int64_t c0 = lo / Lc, c1 = (hi + Lc - 1) / Lc;
+    if (c1 <= c0) return;
+    const int64_t nbv = (hi < h->nb) ? hi + 1 : h->nb;
+#define MV_CB(QQ) chunk_back_kernel<QQ><<<(int)(c1 - c0), 32, 0, h->st>>>(nbv, Lc, c0, h->Dw.p, h->Ew.p, h->ZL.p, h->dsh.p, h->dlt_s.p)
+    switch (h->q) {
+        case 9: MV_CB(9); break;
+        case 12: MV_CB(12); break;
+        case 15: MV_CB(15); break;
+        default: MV_CB(18); break;
+    }
+#undef MV_CB
+    h->launches++;
+}
+
 // Solve the damped system for the current normal equations; delta -> dlt_c / dlt_s.
 // *ok = 0 if a Cholesky pivot was not positive.
 inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
-    const int q = h->q, ldw = h->ldw;
+    const int q = h->q, ldw = h->ldw, Lc = h->Lc;
     const int64_t nb = h->nb, nbq = nb * q;
     const size_t qq = (size_t)q * q;
     const int64_t wn = (int64_t)q * ldw;
@@ -1016,24 +1120,37 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
     double* rhs = h->Sd.p + (size_t)ldw * ldw;
     int* fail_flag = h->flag.p + 1;
     bool timed = false;
+    const bool pre = Lc > 1;
+    // the system the cyclic reduction works on: all super-blocks, or the chunk heads after the pre-reduction
+    double* sD = pre ? h->Dh.p : h->Dw.p;
+    double* sE = pre ? h->Eh.p : h->Ew.p;
+    double* sW = pre ? h->Wh.p : h->Ww.p;
+    double* sZ = pre ? h->ZLh.p : h->ZL.p;
+    double* sd = pre ? h->dsh.p : h->dlt_s.p;
     MV_CUDA(h, cudaMemsetAsync(fail_flag, 0, sizeof(int), h->st));
     MV_CUDA(h, cudaMemsetAsync(h->Sd.p, 0, h->Sd.bytes(), h->st));
     if (h->world <= 1) {
-        // ---------------- single GPU: full cyclic reduction + root ----------------
+        // ---------------- single GPU: (chunk pre-reduction +) full cyclic reduction + root ----------------
         damp_copy_kernel<<<(int)((nbq * q + 255) / 256), 256, 0, h->st>>>(h->D.p, h->diag_s.p, lam, nbq, q,
                                                                           3 * h->n_ctrl, h->Dw.p);
         MV_CUDA(h, cudaMemcpyAsync(h->Ew.p, h->E.p, nb * qq * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
         h->launches += 1;
-        BcrView v{h->Dw.p, h->Ew.p, h->Ww.p, h->ZL.p, h->dlt_s.p, nb};
-        if (h->desc.rs_bounds) {          // frozen columns must be zeroed in a private copy
+        const double* wsrc = h->Wp();          // first touch of every block reads W~ directly: no 2|W~| copy pass
+        if (h->desc.rs_bounds) {               // frozen columns must be zeroed in a private copy
             MV_CUDA(h, cudaMemcpyAsync(h->Ww.p, h->Wp(), (size_t)nbq * ldw * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
             freeze_cols_kernel<<<(int)((nbq + 255) / 256), 256, 0, h->st>>>(h->Ww.p, nbq, ldw, h->nc, h->Pc, h->frozen.p);
             h->launches++;
-        } else {
-            v.Worig = h->Wp();             // first touch of every block reads W~ directly: no 2|W~| copy pass
+            wsrc = h->Ww.p;
         }
         cudaEventRecord(h->evs[0], h->st);
-        std::vector<int64_t> levels = bcr_eliminate(h, v, nb, true, fail_flag);
+        BcrView v{sD, sE, sW, sZ, sd, pre ? h->nh : nb};
+        if (pre) prereduce_range(h, 0, nb, wsrc, fail_flag);
+        else if (!h->desc.rs_bounds) v.Worig = wsrc;
+        std::vector<int64_t> levels = bcr_eliminate(h, v, v.nb, true, fail_flag);
+        if (pre) {                             // the heads' rows join the eliminated ones for the SYRK
+            head_rows_kernel<<<(int)h->nh, 256, 0, h->st>>>(0, Lc, q, ldw, h->Wh.p, h->Ww.p);
+            h->launches++;
+        }
         cudaEventRecord(h->evs[1], h->st);
         launch_syrk(h, h->Ww.p, nbq, h->Sd.p);
         cudaEventRecord(h->evs[2], h->st);
@@ -1044,48 +1161,73 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
         dense_chol_solve(h, h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
         wdc_kernel<<<(int)((nbq * 32 + 255) / 256), 256, 0, h->st>>>(h->Ww.p, h->dlt_c.p, nbq, ldw, h->dlt_s.p);
         h->launches++;
+        if (pre) {
+            wdc_kernel<<<(int)((h->nh * q * 32 + 255) / 256), 256, 0, h->st>>>(h->Wh.p, h->dlt_c.p, h->nh * q, ldw, h->dsh.p);
+            h->launches++;
+        }
         bcr_back(h, v, levels, true);
+        if (pre) chunk_back_range(h, 0, nb);
     } else {
         // ---------------- sharded solve ----------------
-        // Super-blocks are cut into chunks of Bc (power of two); this rank owns chunks [c0, c1).
+        // Super-blocks are cut into chunks of Bc (power of two); this rank owns chunks [c0, c1).  With the
+        // pre-reduction (Lc > 1, Lc divides Bc) the own range is first reduced to its chunk heads; "blocks"
+        // below are then heads and Bc counts heads.
         // Local levels (strides < Bc) run on the view [lo, hi] whose last block is a zeroed GHOST of
-        // the next rank's first block: it collects the left-side Schur updates.  The chunk heads
+        // the next rank's first block: it collects the left-side Schur updates.  The Bc-chunk heads
         // form the top system (nchunks blocks), summed over ranks and eliminated redundantly.
         const int64_t Bc = h->Bc, nchunks = nb / Bc;
         const int64_t c0 = nchunks * h->rank / h->world, c1 = nchunks * (h->rank + 1) / h->world;
         const int64_t lo = c0 * Bc, hi = c1 * Bc, nloc = hi - lo;
+        const int64_t Bs = Bc / Lc, slo = lo / Lc, shi = hi / Lc, sloc = shi - slo;    // the same in units of system blocks
         // damped working copies of the own range; ghost slot zero
+        const double* wsrc = h->Wp();
         if (nloc > 0) {
             damp_copy_kernel<<<(int)((nloc * q * q + 255) / 256), 256, 0, h->st>>>(
                 h->D.p + lo * qq, h->diag_s.p + lo * q, lam, nloc * q, q,
                 std::max<int64_t>(0, 3 * h->n_ctrl - lo * q), h->Dw.p + lo * qq);
             MV_CUDA(h, cudaMemcpyAsync(h->Ew.p + lo * qq, h->E.p + lo * qq, nloc * qq * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-            MV_CUDA(h, cudaMemcpyAsync(h->Ww.p + lo * wn, h->Wp() + lo * wn, (size_t)nloc * wn * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
             h->launches++;
+            if (!pre || h->desc.rs_bounds) {
+                MV_CUDA(h, cudaMemcpyAsync(h->Ww.p + lo * wn, h->Wp() + lo * wn, (size_t)nloc * wn * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+                wsrc = h->Ww.p;
+            }
             if (h->desc.rs_bounds) {
                 freeze_cols_kernel<<<(int)((nloc * q + 255) / 256), 256, 0, h->st>>>(h->Ww.p + lo * wn, nloc * q, ldw, h->nc, h->Pc, h->frozen.p);
                 h->launches++;
             }
         }
-        MV_CUDA(h, cudaMemsetAsync(h->Dw.p + hi * qq, 0, qq * sizeof(double), h->st));
-        MV_CUDA(h, cudaMemsetAsync(h->Ew.p + hi * qq, 0, qq * sizeof(double), h->st));
-        MV_CUDA(h, cudaMemsetAsync(h->Ww.p + hi * wn, 0, wn * sizeof(double), h->st));
-        BcrView lv{h->Dw.p + lo * qq, h->Ew.p + lo * qq, h->Ww.p + lo * wn, h->ZL.p + lo * qq, h->dlt_s.p + lo * q, nloc + 1};
-        std::vector<int64_t> llev;
         cudaEventRecord(h->evs[0], h->st);
-        if (nloc > 0 && Bc > 1) {
-            llev = bcr_eliminate(h, lv, Bc, false, fail_flag);
-            launch_level(h, lv, (int)((lv.nb + Bc - 1) / Bc), Bc, Bc / 2, 2, fail_flag);     // pending updates of the last local level
+        if (pre) {
+            if (nloc > 0) prereduce_range(h, lo, hi, wsrc, fail_flag);      // zeroes the ghost head itself
+            else {
+                MV_CUDA(h, cudaMemsetAsync(sD + shi * qq, 0, qq * sizeof(double), h->st));
+                MV_CUDA(h, cudaMemsetAsync(sE + shi * qq, 0, qq * sizeof(double), h->st));
+                MV_CUDA(h, cudaMemsetAsync(sW + shi * wn, 0, wn * sizeof(double), h->st));
+            }
+        } else {
+            MV_CUDA(h, cudaMemsetAsync(sD + shi * qq, 0, qq * sizeof(double), h->st));
+            MV_CUDA(h, cudaMemsetAsync(sE + shi * qq, 0, qq * sizeof(double), h->st));
+            MV_CUDA(h, cudaMemsetAsync(sW + shi * wn, 0, wn * sizeof(double), h->st));
+        }
+        BcrView lv{sD + slo * qq, sE + slo * qq, sW + slo * wn, sZ + slo * qq, sd + slo * q, sloc + 1};
+        std::vector<int64_t> llev;
+        if (sloc > 0 && Bs > 1) {
+            llev = bcr_eliminate(h, lv, Bs, false, fail_flag);
+            launch_level(h, lv, (int)((lv.nb + Bs - 1) / Bs), Bs, Bs / 2, 2, fail_flag);     // pending updates of the last local level
         }
         // top system
         const size_t tD = (size_t)nchunks * qq, tW = (size_t)nchunks * wn;
         MV_CUDA(h, cudaMemsetAsync(h->Dt.p, 0, (2 * tD + tW) * sizeof(double), h->st));
         double* Dt = h->Dt.p; double* Et = Dt + tD; double* Wt = Et + tD;
-        if (nloc > 0) {
-            top_gather_kernel<<<(int)(c1 - c0 + 1), 128, 0, h->st>>>(h->Dw.p, h->Ew.p, h->Ww.p, q, ldw, Bc, c0, c1, nchunks, Dt, Et, Wt);
+        if (sloc > 0) {
+            top_gather_kernel<<<(int)(c1 - c0 + 1), 128, 0, h->st>>>(sD, sE, sW, q, ldw, Bs, c0, c1, nchunks, Dt, Et, Wt);
             h->launches++;
             // chunk heads leave the local system: their rows must not enter the local SYRK
-            MV_CUDA(h, cudaMemset2DAsync(h->Ww.p + lo * wn, (size_t)Bc * wn * sizeof(double), 0, wn * sizeof(double), (size_t)(c1 - c0), h->st));
+            MV_CUDA(h, cudaMemset2DAsync(sW + slo * wn, (size_t)Bs * wn * sizeof(double), 0, wn * sizeof(double), (size_t)(c1 - c0), h->st));
+            if (pre) {                         // the local heads' rows join the eliminated ones (Ww) for the SYRK
+                head_rows_kernel<<<(int)sloc, 256, 0, h->st>>>(slo, Lc, q, ldw, h->Wh.p, h->Ww.p);
+                h->launches++;
+            }
         }
         int e = nccl_sum(h, Dt, 2 * tD + tW);
         if (e) return e;
@@ -1105,15 +1247,21 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
         dense_chol_solve(h, h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
         e = nccl_bcast0(h, h->dlt_c.p, (size_t)h->ncP);
         if (e) return e;
-        // back substitution: top system (redundant), then the local levels
+        // back substitution: top system (redundant), then the local levels, then inside the chunks
         wdc_kernel<<<(int)((nchunks * q * 32 + 255) / 256), 256, 0, h->st>>>(Wt, h->dlt_c.p, nchunks * q, ldw, h->dst.p);
         h->launches++;
         bcr_back(h, tv, tlev, true);
         if (nloc > 0) {
             wdc_kernel<<<(int)((nloc * q * 32 + 255) / 256), 256, 0, h->st>>>(h->Ww.p + lo * wn, h->dlt_c.p, nloc * q, ldw, h->dlt_s.p + lo * q);
-            top_scatter_kernel<<<(int)(c1 - c0 + 1), 32, 0, h->st>>>(h->dst.p, q, Bc, c0, c1, nchunks, h->dlt_s.p);
-            h->launches += 2;
+            h->launches++;
+            if (pre) {
+                wdc_kernel<<<(int)((sloc * q * 32 + 255) / 256), 256, 0, h->st>>>(sW + slo * wn, h->dlt_c.p, sloc * q, ldw, sd + slo * q);
+                h->launches++;
+            }
+            top_scatter_kernel<<<(int)(c1 - c0 + 1), 32, 0, h->st>>>(h->dst.p, q, Bs, c0, c1, nchunks, sd);
+            h->launches++;
             bcr_back(h, lv, llev, false);
+            if (pre) chunk_back_range(h, lo, hi);
         }
         zero_outside_kernel<<<(int)(((nbq + q) + 255) / 256), 256, 0, h->st>>>(h->dlt_s.p, nbq + q, lo * q, hi * q);
         h->launches++;

@@ -13,6 +13,7 @@
 
 #include "ba_ctx.cuh"
 #include "ba_kernels.cuh"
+#include "ba_chunk.cuh"
 #include "ba_solve.cuh"
 #include "ba_nccl.cuh"
 #include "ba_bookkeeping.cuh"
@@ -84,6 +85,7 @@ extern "C" int mvus_ba_create(const mvus_ba_desc* desc, mvus_ba_handle* out) {
     h->verbose = getenv("MVUS_BA_VERBOSE") != nullptr;              // diagnostics: read here, once, not inside the solve
     if (getenv("MVUS_BA_BAND_LO")) h->band_lo = atof(getenv("MVUS_BA_BAND_LO"));
     if (getenv("MVUS_BA_BAND_HI")) h->band_hi = atof(getenv("MVUS_BA_BAND_HI"));
+    h->Lc_req = desc->solver_chunk;
     h->desc = *desc;
     h->nc = desc->num_cams;
     h->C = desc->opt_calib ? 15 : 6;
@@ -112,7 +114,8 @@ extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
                     &h->int_b, &h->knots, &h->spanpoly, &h->span_t0, &h->lut_t0, &h->lut_invh, &h->tau,
                     &h->x, &h->x_trial, &h->camprep, &h->r, &h->J, &h->mJ, &h->partial, &h->A, &h->D, &h->E,
                     &h->W, &h->Dw, &h->Ew, &h->Ww, &h->ZL, &h->Sd, &h->dlt_c, &h->dlt_s, &h->diag_c,
-                    &h->diag_s, &h->gvec, &h->xs, &h->scratch, &h->gt_out, &h->Dt, &h->ZLt, &h->dst, &h->bs, &h->Hb})
+                    &h->diag_s, &h->gvec, &h->xs, &h->scratch, &h->gt_out, &h->Dt, &h->ZLt, &h->dst, &h->bs, &h->Hb,
+                    &h->Dh, &h->Eh, &h->Wh, &h->ZLh, &h->dsh, &h->DhR, &h->Gh, &h->Linv})
         b->release(false);
     for (auto* b : {&h->row_off, &h->tile_start, &h->knot_off, &h->ctrl_off, &h->xoff, &h->lut_off}) b->release(false);
     for (auto* b : {&h->tile_cam, &h->tile_cnt, &h->ncoef, &h->deg, &h->lut_n, &h->lut, &h->tau_spl, &h->span,

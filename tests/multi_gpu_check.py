@@ -25,11 +25,12 @@ rank, world = dist.get_rank(), dist.get_world_size()
 ba.DEVICE = local
 shard.init_comm()
 ok_all = True
+CHUNK = int(os.environ.get('MVUS_TEST_CHUNK', '0'))     # force the solver's pre-reduction chunk length
 for name in ('rs_F_gap', 'calib_KE', 'gs_plain'):
-    fl, truth, bakw = cases.make(name, det_per_cam=3000)
+    fl, truth, bakw = cases.make(name, det_per_cam=int(os.environ.get('MVUS_TEST_DET', '3000')))
     # single-GPU reference on every rank (no communicator)
     fp = FlatProblem(fl, fl.numCam, **bakw)
-    h1 = _cabi.Handle(fp, device=local, max_nfev=12)
+    h1 = _cabi.Handle(fp, device=local, max_nfev=12, solver_chunk=1)
     x1, r1, s1 = h1.solve(fp.x0)
     A1, g1, _, _, c1 = h1.normal_equations(fp.x0, want_dense=False)
     h1.close()
@@ -37,7 +38,7 @@ for name in ('rs_F_gap', 'calib_KE', 'gs_plain'):
         bounds = shard.shard_bounds(fl, world, motion_reg=bakw.get('motion_reg', False)) if mode == 'span' else None
         loc = shard.shard_scene(fl, rank, world, bounds)
         fpl = FlatProblem(loc, loc.numCam, **bakw)
-        hN = _cabi.Handle(fpl, device=local, max_nfev=12)
+        hN = _cabi.Handle(fpl, device=local, max_nfev=12, solver_chunk=CHUNK)
         hN.comm_init(*ba._COMM)
         AN, gN, _, _, cN = hN.normal_equations(fpl.x0, want_dense=False)
         xN, rN, sN = hN.solve(fpl.x0)

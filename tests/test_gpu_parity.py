@@ -127,6 +127,30 @@ def test_cost_not_above_shipped(name, built_lib):
     hd.close()
 
 
+@pytest.mark.parametrize('name', ['gs_plain', 'rs_F_gap', 'calib_KE', 'rs_bounds_dense'])
+def test_chunk_prereduction_is_the_same_solve(name, built_lib):
+    """The chunk pre-reduction in front of the cyclic reduction (csrc/ba_chunk.cuh, desc.solver_chunk) is
+    an exact reordering of the same elimination: a 4-evaluation and a 10-evaluation solve must agree with the
+    cyclic-reduction-only solve (chunk lengths that divide the block count and ragged ones)."""
+    fl, fp, prob, _ = _setup(name)
+    base1 = base10 = None
+    for chunk in (1, 2, 5, 64):
+        h1 = _cabi.Handle(fp, max_nfev=4, solver_chunk=chunk)
+        x1, _, s1 = h1.solve(fp.x0)
+        h1.close()
+        h10 = _cabi.Handle(fp, max_nfev=10, solver_chunk=chunk)
+        x10, _, s10 = h10.solve(fp.x0)
+        h10.close()
+        if chunk == 1:
+            base1, base10 = (x1, s1), (x10, s10)
+            continue
+        step = np.abs(base1[0] - fp.x0).max()
+        assert step > 0 and s1.nfev == base1[1].nfev
+        assert np.abs(x1 - base1[0]).max() <= 1e-7 * step, (chunk, np.abs(x1 - base1[0]).max(), step)
+        assert s10.nfev == base10[1].nfev
+        assert abs(s10.cost - base10[1].cost) <= 1e-7 * base10[1].cost, (chunk, s10.cost, base10[1].cost)
+
+
 @pytest.mark.parametrize('name', ['gs_margin', 'rs_KE_fpk30'])
 def test_cost_parity_converged(name, built_lib):
     """Two-sided check against oracle B (exact-Jacobian SciPy TRF on the same error function,
