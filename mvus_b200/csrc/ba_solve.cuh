@@ -274,7 +274,7 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, int odd_o
 // that 576 = 18 x 32 columns need no padding strip.
 // History: v1 4x4 scalar micro-tiles 4.4 TFLOP/s, v2 8x8 scalar 6.2 TFLOP/s, v3 FP64 MMA with a
 // single-buffered register-prefetch pipeline 23 TFLOP/s issued (DMMA pipe 60 %; profiles/r1_notes.md).
-constexpr int SY_T = 128, SY_K = 16, SY_LD = SY_T + 4, SY_STAGES = 4;
+constexpr int SY_T = 128, SY_K = 32, SY_LD = SY_T + 4, SY_STAGES = 3, SY_NQ = SY_K / 4;
 constexpr size_t SY_SMEM = (size_t)SY_STAGES * 2 * SY_K * SY_LD * sizeof(double);
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
@@ -286,14 +286,18 @@ __device__ __forceinline__ void sy_cp8(unsigned dst, const double* src, bool ok)
 }
 
 __global__ void __launch_bounds__(512)
-syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, double* __restrict__ Sfull) {
+syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, int nbig, int small,
+            double* __restrict__ Sfull) {
     extern __shared__ __align__(16) double sy_smem[];
     int p = blockIdx.x, ti = 0;
     while (p >= ti + 1) { p -= ti + 1; ++ti; }
     const int tj = p;
     const bool diag = (ti == tj);
-    const int64_t r0 = (int64_t)blockIdx.y * slab;
-    const int64_t r1 = r0 + slab < R ? r0 + slab : R;
+    // row slab: nbig slabs of `slab` rows, then slabs of `small` rows (launch_syrk)
+    const int by = (int)blockIdx.y;
+    const int64_t r0 = by < nbig ? (int64_t)by * slab : (int64_t)nbig * slab + (int64_t)(by - nbig) * small;
+    const int64_t r1e = r0 + (by < nbig ? slab : small);
+    const int64_t r1 = r1e < R ? r1e : R;
     const int nchunk = (int)((r1 - r0 + SY_K - 1) / SY_K);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // 4 x 4 warps of 32 x 32.  Warp w issues on scheduler w & 3: in a diagonal tile pair only the warp
@@ -332,30 +336,39 @@ syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, 
     const double* pa = Ww + (r0 + kq) * ldw + (cola ? ti * SY_T + cc : 0);
     const double* pb = Ww + (r0 + kq) * ldw + (colb ? tj * SY_T + cc : 0);
     const unsigned soff = (unsigned)(kq * SY_LD + cc) * 8u;
-    const int64_t ld4 = 4 * (int64_t)ldw, ld16 = 16 * (int64_t)ldw;
+    const int64_t ld4 = 4 * (int64_t)ldw, ld16 = SY_K * (int64_t)ldw;
     const int nfull = (int)((r1 - r0) / SY_K);             // chunks whose 16 rows all exist
-    auto issue = [&](int c) {
+    // Pipeline synchronisation without a CTA-wide rendezvous: full[st] completes when all 512 threads' copies
+    // of the chunk in stage st have landed (cp.async.mbarrier.arrive.noinc), empty[st] when all 16 warps have
+    // finished reading it.  Warps drift apart by up to a chunk, so the FP64-MMA pipe of a scheduler always has
+    // a warp with queued work (with __syncthreads per chunk it ran dry at every barrier: 7.7 ms -> see notes).
+    __shared__ __align__(8) unsigned long long sy_bar[2 * SY_STAGES];
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(sy_bar);
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < SY_STAGES; ++st) { k2_mbar_init(bar0 + 8u * st, 512u); k2_mbar_init(bar0 + 8u * (SY_STAGES + st), 16u); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // quarter k of the copies of chunk c (row kq + 4k of both panels)
+    auto issue_q = [&](int c, int k) {
         if (c < nchunk) {
-            const unsigned sa = sbase + (unsigned)(c % SY_STAGES) * STAGE_B + soff;
-            if (c < nfull) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa + k * ROW4_B), "l"(pa + k * ld4), "r"(sza) : "memory");
-                    if (!diag)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa + PANEL_B + k * ROW4_B), "l"(pb + k * ld4), "r"(szb) : "memory");
-                }
-            } else {                                       // last, partial chunk of the slab: rows past r1 are zero-filled
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const bool inr = r0 + (int64_t)c * SY_K + kq + 4 * k < r1;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa + k * ROW4_B), "l"(inr ? pa + k * ld4 : Ww), "r"(inr ? sza : 0u) : "memory");
-                    if (!diag)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa + PANEL_B + k * ROW4_B), "l"(inr ? pb + k * ld4 : Ww), "r"(inr ? szb : 0u) : "memory");
-                }
+            const int st = c % SY_STAGES;
+            if (k == 0 && c >= SY_STAGES) k2_mbar_wait(bar0 + 8u * (SY_STAGES + st), (unsigned)((c / SY_STAGES - 1) & 1));
+            const unsigned sa = sbase + (unsigned)st * STAGE_B + soff + k * ROW4_B;
+            const bool inr = c < nfull || r0 + (int64_t)c * SY_K + kq + 4 * k < r1;   // rows past r1 are zero-filled
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa), "l"(inr ? pa + k * ld4 : Ww), "r"(inr ? sza : 0u) : "memory");
+            if (!diag)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa + PANEL_B), "l"(inr ? pb + k * ld4 : Ww), "r"(inr ? szb : 0u) : "memory");
+            if (k == SY_NQ - 1) {
+                pa += ld16; pb += ld16;
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(bar0 + 8u * st) : "memory");
             }
-            pa += ld16; pb += ld16;
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto issue = [&](int c) {
+#pragma unroll
+        for (int k = 0; k < SY_NQ; ++k) issue_q(c, k);
     };
     auto mma_step = [&](const double* As, const double* Bp, int ks) {
         double a[4], b[4];
@@ -372,17 +385,20 @@ syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, 
 #pragma unroll
     for (int c = 0; c < SY_STAGES - 1; ++c) issue(c);
     for (int c = 0; c < nchunk; ++c) {
-        asm volatile("cp.async.wait_group %0;" :: "n"(SY_STAGES - 2) : "memory");
-        __syncthreads();                       // chunk c has landed for everybody; stage (c - 1) % STAGES is free
-        const double* As = sy_smem + (size_t)(c % SY_STAGES) * 2 * SY_K * SY_LD;
+        const int st = c % SY_STAGES;
+        k2_mbar_wait(bar0 + 8u * st, (unsigned)((c / SY_STAGES) & 1));        // chunk c has landed
+        const double* As = sy_smem + (size_t)st * 2 * SY_K * SY_LD;
         const double* Bp = diag ? As : As + SY_K * SY_LD;
-        // the first quarter of the chunk's MMAs is queued BEFORE the copies of chunk c + 3 are issued, so the
-        // FP64-MMA pipe has work while the warps of this scheduler run through their staging instructions
-        if (warp_active) mma_step(As, Bp, 0);
-        issue(c + SY_STAGES - 1);
-        if (warp_active) {
+        // each quarter of the chunk's MMAs is queued BEFORE a quarter of the copies of chunk c + STAGES - 1 is
+        // issued, so the FP64-MMA pipe has work while this warp runs through its staging instructions
 #pragma unroll
-            for (int ks = 4; ks < SY_K; ks += 4) mma_step(As, Bp, ks);
+        for (int k = 0; k < SY_NQ; ++k) {
+            if (warp_active) mma_step(As, Bp, 4 * k);
+            if (k == SY_NQ - 1) {              // this warp is done with stage st
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar0 + 8u * (SY_STAGES + st)) : "memory");
+            }
+            issue_q(c + SY_STAGES - 1, k);
         }
     }
 #pragma unroll
@@ -1008,14 +1024,19 @@ inline void launch_syrk(mvus_ba_ctx* h, const double* Wrows, int64_t R, double* 
     if (R <= 0) return;
     const int ldw = h->ldw, n = h->ncP;
     const int nts = (n + SY_T - 1) / SY_T, npairs = nts * (nts + 1) / 2;
-    // ~8 waves of CTAs over the SMs (one 512-thread CTA per SM; CTA durations differ by up to 16:6 active
-    // warp tiles, so few waves leave a tail of most of a CTA duration), slabs a multiple of the K chunk
-    int64_t nslab = std::max<int64_t>(1, (8 * h->sm_count + npairs - 1) / npairs);
-    int slab = (int)std::max<int64_t>(256, ((R + nslab - 1) / nslab + SY_K - 1) / SY_K * SY_K);
-    dim3 g(npairs, (unsigned)((R + slab - 1) / slab));
+    // one 512-thread CTA per SM; CTA durations differ by up to 16:3 active warp tiles; slabs are multiples of the K chunk
+    // CTAs are dispatched in order as SMs free up, so the launch ends with a tail of up to one CTA duration:
+    // the first 3/4 of the rows go in big slabs (~6 waves), the last quarter in slabs a quarter as long
+    int64_t nbig = std::max<int64_t>(1, (6 * h->sm_count + npairs - 1) / npairs);
+    int slab = (int)std::max<int64_t>(256, ((R * 3 / 4 + nbig - 1) / nbig + SY_K - 1) / SY_K * SY_K);
+    nbig = std::min<int64_t>(nbig, R / slab);
+    const int small = std::max(64, slab / 4 / SY_K * SY_K);
+    const int64_t rest = R - nbig * slab;
+    const int64_t nsmall = (rest + small - 1) / small;
+    dim3 g(npairs, (unsigned)(nbig + nsmall));
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM); attr_set = true; }
-    syrk_kernel<<<g, 512, SY_SMEM, h->st>>>(Wrows, R, ldw, n, slab, Sfull);
+    syrk_kernel<<<g, 512, SY_SMEM, h->st>>>(Wrows, R, ldw, n, slab, (int)nbig, small, Sfull);
     const int rslab = 128;                                 // rows per CTA of the right-hand-side GEMV
     wtw_rhs_kernel<<<(int)((R + rslab - 1) / rslab), RHS_T, 0, h->st>>>(Wrows, R, ldw, n, rslab, Sfull);
     h->launches += 2;
