@@ -187,6 +187,20 @@ int mvus_ba_global_traj(mvus_ba_handle h, const double* x, const int32_t* cam_id
 int mvus_ba_spline_to_traj(mvus_ba_handle h, const double* x, const double* t, int64_t n,
                            int64_t* n_out, double* out);
 
+/* Ground-truth alignment (analysis/compare_gt.py:35-70, 112-126; thirdparty/transformation.py:869-975
+ * affine_matrix_from_points(shear=False, scale=True)): nshift independent similarity fits between the
+ * splines of the handle (coefficients inside x), evaluated at tau[j] + shift[b], and the fixed points
+ * pts (3 x n row-major).  A point takes part iff its shifted time lies in a spline interval by the rule
+ * of util.sampling (a <= t < b, util.py:105).  spline_is_src != 0: the transform maps the spline points
+ * onto pts (fine stage, error_fn of compare_gt.optimize); 0: pts onto the spline points (coarse search,
+ * where the spline is the interpolating spline of the ground truth, util.match_overlap).
+ * Outputs per shift: mean_err (mean point distance after the fit; +inf when fewer than 3 points take
+ * part, where the reference raises), count, M (4 x 4 row-major).  err (may be NULL): the n point
+ * distances of shift number `want`, 0 where the point takes no part.  Needs mvus_ba_set_splines only. */
+int mvus_ba_align(mvus_ba_handle h, const double* x, int64_t n, const double* tau, const double* pts,
+                  int32_t nshift, const double* shift, int32_t spline_is_src, int32_t want,
+                  double* mean_err, int64_t* count, double* M, double* err);
+
 /* Diagnostics used by the parity tests: the normal equations K2 assembles at x.
  *   A    [nc*Pc*Pc]  camera diagonal blocks (Pc = 3 + C), row-major per camera
  *   g    [n]         J^T r in the reference's x layout

@@ -43,7 +43,7 @@ EXPORTS = ['mvus_ba_version', 'mvus_ba_create', 'mvus_ba_destroy', 'mvus_ba_last
            'mvus_ba_normal_equations', 'mvus_ba_global_traj', 'mvus_ba_spline_to_traj', 'mvus_ba_visibility', 'mvus_ba_host_alloc',
            'mvus_ba_host_free', 'mvus_ba_trim', 'mvus_ba_nccl_unique_id', 'mvus_ba_comm_init', 'mvus_ba_shard_bounds',
            'mvus_ba_time_resjac', 'mvus_ba_time_accumulate', 'mvus_ba_spl_create', 'mvus_ba_spl_destroy',
-           'mvus_ba_spl_last_error', 'mvus_ba_spl_solve']
+           'mvus_ba_spl_last_error', 'mvus_ba_spl_solve', 'mvus_ba_align']
 
 _lib = None
 
@@ -79,6 +79,8 @@ def load():
     lib.mvus_ba_normal_equations.argtypes = [ctypes.c_void_p, _dp, _dp, _dp, _dp, _ip, _dp, _dp]
     lib.mvus_ba_global_traj.argtypes = [ctypes.c_void_p, _dp, _ip, _lp, _dp, _dp]
     lib.mvus_ba_spline_to_traj.argtypes = [ctypes.c_void_p, _dp, _dp, ctypes.c_int64, _lp, _dp]
+    lib.mvus_ba_align.argtypes = [ctypes.c_void_p, _dp, ctypes.c_int64, _dp, _dp, ctypes.c_int32, _dp, ctypes.c_int32,
+                                  ctypes.c_int32, _dp, _lp, _dp, _dp]
     lib.mvus_ba_visibility.argtypes = [ctypes.c_void_p, _dp, _lp]
     lib.mvus_ba_host_alloc.argtypes = [ctypes.c_size_t]
     lib.mvus_ba_host_alloc.restype = ctypes.c_void_p
@@ -282,6 +284,21 @@ class Handle:
         n = ctypes.c_int64()
         self._check(self.lib.mvus_ba_global_traj(self.h, _d(x), _i(ids), ctypes.byref(n), _d(out), _d(gd)))
         return out[:7 * n.value].reshape(7, n.value), gd[:3 * self.N].reshape(3, self.N)
+
+    def align(self, x, tau, pts, shifts, spline_is_src, want=-1):
+        """mvus_ba_align: one similarity fit per shift between the handle's splines at tau + shift and the 3 x n
+        points.  -> (mean_err [nshift], count [nshift], M [nshift, 4, 4], err [n] or None)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        tau = np.ascontiguousarray(tau, dtype=np.float64)
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        shifts = np.ascontiguousarray(np.atleast_1d(shifts), dtype=np.float64)
+        n, ns = len(tau), len(shifts)
+        assert pts.shape == (3, n)
+        mean_err, count, M = np.empty(ns), np.empty(ns, dtype=np.int64), np.empty((ns, 4, 4))
+        err = np.empty(n) if want >= 0 else None
+        self._check(self.lib.mvus_ba_align(self.h, _d(x), n, _d(tau), _d(pts), ns, _d(shifts), int(bool(spline_is_src)),
+                                           int(want), _d(mean_err), _l(count), _d(M), _d(err)))
+        return mean_err, count, M, err
 
     def normal_equations(self, x, want_dense=True):
         fp = self.fp

@@ -18,6 +18,7 @@
 #include "ba_nccl.cuh"
 #include "ba_bookkeeping.cuh"
 #include "spl_fit.cuh"
+#include "align.cuh"
 
 using namespace mvus;
 
@@ -991,6 +992,42 @@ extern "C" int mvus_ba_spline_to_traj(mvus_ba_handle h, const double* x, const d
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
     }
+    cleanup();
+    if (e != cudaSuccess) return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e));
+    return MVUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" int mvus_ba_align(mvus_ba_handle h, const double* x, int64_t n, const double* tau, const double* pts,
+                             int32_t nshift, const double* shift, int32_t spline_is_src, int32_t want,
+                             double* mean_err, int64_t* count, double* M, double* err) {
+    if (!h) return MVUS_ERR_ARG;
+    if (!h->have_spl) return fail(h, MVUS_ERR_ARG, "set_splines first");
+    if (!x || !tau || !pts || !shift || !mean_err || !count || !M || n < 1 || nshift < 1)
+        return fail(h, MVUS_ERR_ARG, "null or empty argument");
+    MV_CUDA(h, cudaSetDevice(h->desc.device));
+    const int64_t nx = h->n_other + 3 * h->n_ctrl;
+    DevBuf<double> xd, td, pd, sd, me, Md, ed;
+    DevBuf<int64_t> cd;
+    auto cleanup = [&]() { xd.release(); td.release(); pd.release(); sd.release(); me.release(); Md.release(); ed.release(); cd.release(); };
+    cudaError_t e = upload(xd, x, (size_t)nx, h->st);
+    if (e == cudaSuccess) e = upload(td, tau, (size_t)n, h->st);
+    if (e == cudaSuccess) e = upload(pd, pts, (size_t)3 * n, h->st);
+    if (e == cudaSuccess) e = upload(sd, shift, (size_t)nshift, h->st);
+    if (e == cudaSuccess) e = me.alloc(nshift);
+    if (e == cudaSuccess) e = Md.alloc((size_t)16 * nshift);
+    if (e == cudaSuccess) e = cd.alloc(nshift);
+    if (e == cudaSuccess && err) e = ed.alloc(n);
+    if (e == cudaSuccess) {
+        align_fit_kernel<<<nshift, AL_T, 0, h->st>>>(h->sv, xd.p, td.p, pd.p, n, sd.p, spline_is_src, err ? want : -1,
+                                                     me.p, cd.p, Md.p, err ? ed.p : nullptr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mean_err, me.p, nshift * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(count, cd.p, nshift * sizeof(int64_t), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(M, Md.p, (size_t)16 * nshift * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess && err) e = cudaMemcpyAsync(err, ed.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
     cleanup();
     if (e != cudaSuccess) return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e));
     return MVUS_OK;

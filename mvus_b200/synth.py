@@ -210,9 +210,11 @@ def make_flight(nc=4, det_per_cam=1500, frames_per_knot=15.0, seed=0, noise=0.5,
 
 
 def write_dataset(out_dir, nc=4, det_per_cam=5000, seed=0, noise=0.5, rolling_shutter=False,
-                  distortion=False, settings=None):
+                  distortion=False, settings=None, ground_truth=None):
     """Write a dataset4-format flight (detections ``x y frame``, camera JSON, config JSON)
-    that the reference ``main.py`` runs end to end; returns the config path."""
+    that the reference ``main.py`` runs end to end; returns the config path.  ``ground_truth`` = a frequency in
+    Hz adds an RTK-style ground-truth file (the true trajectory in another similarity frame, 2 cm noise, longer
+    than the flight) under 'optional inputs' so that main.py:88-90 calls align_gt."""
     os.makedirs(out_dir, exist_ok=True)
     rng_f = np.random.default_rng(seed)
     rng_n = np.random.default_rng(seed + 1)
@@ -252,6 +254,19 @@ def write_dataset(out_dir, nc=4, det_per_cam=5000, seed=0, noise=0.5, rolling_sh
            'necessary inputs': {'path_detections': det_paths, 'path_cameras': cam_paths,
                                 'corresponding_frames': cf.tolist()},
            'settings': st}
+    if ground_truth:
+        tau = np.arange(-6.0 * fps_ref, T + 9.0 * fps_ref, fps_ref / float(ground_truth))
+        # a proper rotation (Rodrigues of a fixed vector), scale 1.7, offset
+        w = np.array([0.3, -0.2, 0.5])
+        th = np.linalg.norm(w)
+        k = w / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+        Y = 1.7 * R @ gt_trajectory(tau, fps_ref=fps_ref) + np.array([[10.0], [-4.0], [2.5]])
+        Y = Y + np.random.default_rng(seed + 5).normal(size=Y.shape) * 0.02
+        gp = os.path.join(out_dir, 'gt.txt')
+        np.savetxt(gp, Y.T)
+        cfg['optional inputs'] = {'ground_truth': {'filepath': gp, 'frequency': float(ground_truth)}}
     p = os.path.join(out_dir, 'config.json')
     with open(p, 'w') as fh:
         json.dump(cfg, fh, indent=1)

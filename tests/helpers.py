@@ -159,3 +159,24 @@ def check_normal_equations(fp, prob, x, A, g, Hss, Hcs, cost, rtol=1e-9, n_sampl
     # nothing outside the band: the rows further than `band` control points apart are orthogonal
     far = Js[:, :3].T @ Js[:, 3 * band:] if fp.n_ctrl > band else None
     assert far is None or abs(far).max() == 0.0
+
+
+def make_alignment_case(name='rs_F_gap', det_per_cam=400, f_gt=5.0, seed=7, with_time=True):
+    """A flight plus a synthetic RTK ground truth for analysis/compare_gt.align_gt: the true trajectory at
+    f_gt Hz over a wider time span than the flight, similarity-transformed (scale, rotation, translation) with
+    2 cm noise.  -> (flight, gt array 4 x n [time in GT samples' own clock; X; Y; Z] or 3 x n, f_gt)."""
+    import cases
+    from mvus_b200 import hostmath, synth
+    fl, truth, _ = cases.make(name, det_per_cam=det_per_cam, perturb=0.0)
+    fl.settings['ref_cam'] = fl.ref_cam
+    rng = np.random.default_rng(seed)
+    fps = fl.cameras[fl.ref_cam].fps
+    interval = np.asarray(fl.spline['int'])
+    t_lo, t_hi = interval[0, 0] - 6.0 * fps, interval[1, -1] + 9.0 * fps          # frames of the reference camera
+    tau = np.arange(t_lo, t_hi, fps / f_gt)
+    X = synth.gt_trajectory(tau, fps_ref=fps)
+    R = hostmath.rodrigues_to_matrix(np.array([0.3, -0.2, 0.5]))
+    Y = 1.7 * R @ X + np.array([[10.0], [-4.0], [2.5]]) + rng.normal(size=X.shape) * 0.02
+    if with_time:
+        return fl, np.vstack((100.0 + np.arange(len(tau)), Y)), f_gt
+    return fl, Y, f_gt

@@ -173,8 +173,8 @@ def test_main_py_through_the_dropin(built_lib, tmp_path):
     detections per camera so that the untouched reference finishes in ~15 s): main.py:18-97 runs
     unmodified twice on the same dataset4-format files -- once as shipped (SciPy BA on the CPU),
     once with mvus_b200.dropin.install (every BA / error_cam / remove_outliers on the B200)."""
-    cfg_ref = synth.write_dataset(str(tmp_path / 'ref'), nc=4, det_per_cam=1500, seed=0)
-    cfg_gpu = synth.write_dataset(str(tmp_path / 'gpu'), nc=4, det_per_cam=1500, seed=0)
+    cfg_ref = synth.write_dataset(str(tmp_path / 'ref'), nc=4, det_per_cam=1500, seed=0, ground_truth=5)
+    cfg_gpu = synth.write_dataset(str(tmp_path / 'gpu'), nc=4, det_per_cam=1500, seed=0, ground_truth=5)
     f_ref, log_ref = ref_shim.run_main(cfg_ref)
     f_gpu, log_gpu = ref_shim.run_main(cfg_gpu, install=dropin.install, uninstall=dropin.uninstall)
     assert 'Finished!' in log_ref and 'Finished!' in log_gpu
@@ -194,6 +194,15 @@ def test_main_py_through_the_dropin(built_lib, tmp_path):
               'traj', 'sequence', 'visible', 'settings', 'out'):
         assert hasattr(back, k), k
     assert type(back).__module__ == 'reconstruction.common'
+    # main.py:88-90: align_gt against the RTK-style ground truth (through the drop-in: mvus_b200.align on the GPU)
+    for f in (f_ref, back):
+        assert set(f.out) == {'align_param', 'reconst_tran', 'gt', 'tran_matrix', 'error'}
+        assert f.out['reconst_tran'].shape[0] == 4 and f.out['gt'].shape[0] == 3
+    fps0 = back.cameras[back.settings['ref_cam']].fps                      # alpha ~ reference-camera fps / 5 Hz
+    assert abs(back.out['align_param'][0] - fps0 / 5.0) < 0.01 * fps0 / 5.0
+    assert abs(back.out['align_param'][0] - f_ref.out['align_param'][0]) < 0.01 * fps0 / 5.0
+    assert np.mean(back.out['error']) <= 1.1 * np.mean(f_ref.out['error']) + 0.02, (
+        np.mean(back.out['error']), np.mean(f_ref.out['error']))
     assert back.traj.shape[0] == 4 and back.traj.shape[1] > 100
     assert len(back.detections_global) == 4 and all(d.shape[0] == 3 for d in back.detections_global)
     for c in back.cameras:
