@@ -201,6 +201,30 @@ int mvus_ba_align(mvus_ba_handle h, const double* x, int64_t n, const double* ta
                   int32_t nshift, const double* shift, int32_t spline_is_src, int32_t want,
                   double* mean_err, int64_t* count, double* M, double* err);
 
+/* Scene.BA(motion_prior=True): the discrete-trajectory mode (common.py:466-467, 527-550, 587-605, 631-634,
+ * 681-687).  Unknowns = camera side + the G points of global_traj (common.py:887-944); the splines are
+ * constants; motion rows of error_motion(motion_prior=True) (common.py:386-403) tie consecutive points of a
+ * spline interval together, with time stamps that follow alpha/beta/rho of the camera that saw each point.
+ * Two handles: hs = the ordinary handle of the flight (detections + splines, motion_type NONE), hp = a handle
+ * with the same cameras, NO detections and ONE pseudo-spline of degree 1 with G coefficients (it only sizes the
+ * block-tridiagonal solver for G points; the LM controls -- max_nfev, tolerances, rs_bounds -- are hp's).
+ *   mvus_ba_points_set   per point: camera slot (position in sequence[:numCam]), frame id and raw y / image
+ *                        height of its detection.
+ *   x layout of hp       [alpha, beta, rho, camera vectors | X_0..X_G-1 | Y_0.. | Z_0..]  (the reference's
+ *                        vector interleaves the points, common.py:631-634; the binding converts)
+ *   xs0                  a parameter vector of hs (reference layout): its spline coefficients are the constants
+ *   r_out                2N reprojection rows in the reference's order, then G motion rows in global_traj order
+ *                        (row j = the triple centred at point j for F, the pair ending at j for KE)
+ * A motion row may span at most 4 consecutive points (MVUS_ERR_UNSUPPORTED otherwise).  One GPU. */
+int mvus_ba_points_set(mvus_ba_handle hp, int64_t G, const int32_t* cam_slot, const double* frame,
+                       const double* y_over_height);
+int mvus_ba_solve_points(mvus_ba_handle hs, mvus_ba_handle hp, int32_t motion_type, double motion_weight,
+                         const double* xs0, const double* x0, double* x_out, double* r_out,
+                         mvus_ba_stats* stats);
+/* diagnostics for the parity tests: residual vector, gradient J^T r (hp layout) and cost at x */
+int mvus_ba_points_eval(mvus_ba_handle hs, mvus_ba_handle hp, int32_t motion_type, double motion_weight,
+                        const double* xs0, const double* x, double* r_out, double* g_out, double* cost);
+
 /* Diagnostics used by the parity tests: the normal equations K2 assembles at x.
  *   A    [nc*Pc*Pc]  camera diagonal blocks (Pc = 3 + C), row-major per camera
  *   g    [n]         J^T r in the reference's x layout

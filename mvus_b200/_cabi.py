@@ -43,7 +43,8 @@ EXPORTS = ['mvus_ba_version', 'mvus_ba_create', 'mvus_ba_destroy', 'mvus_ba_last
            'mvus_ba_normal_equations', 'mvus_ba_global_traj', 'mvus_ba_spline_to_traj', 'mvus_ba_visibility', 'mvus_ba_host_alloc',
            'mvus_ba_host_free', 'mvus_ba_trim', 'mvus_ba_nccl_unique_id', 'mvus_ba_comm_init', 'mvus_ba_shard_bounds',
            'mvus_ba_time_resjac', 'mvus_ba_time_accumulate', 'mvus_ba_spl_create', 'mvus_ba_spl_destroy',
-           'mvus_ba_spl_last_error', 'mvus_ba_spl_solve', 'mvus_ba_align']
+           'mvus_ba_spl_last_error', 'mvus_ba_spl_solve', 'mvus_ba_align', 'mvus_ba_points_set',
+           'mvus_ba_solve_points', 'mvus_ba_points_eval']
 
 _lib = None
 
@@ -299,6 +300,39 @@ class Handle:
         self._check(self.lib.mvus_ba_align(self.h, _d(x), n, _d(tau), _d(pts), ns, _d(shifts), int(bool(spline_is_src)),
                                            int(want), _d(mean_err), _l(count), _d(M), _d(err)))
         return mean_err, count, M, err
+
+    # ---- Scene.BA(motion_prior=True): this handle is the POINTS handle (see include/mvus_ba.h) ----
+    def points_set(self, cam_slot, frame, y_over_height):
+        cam_slot = np.ascontiguousarray(cam_slot, dtype=np.int32)
+        frame = np.ascontiguousarray(frame, dtype=np.float64)
+        yh = np.ascontiguousarray(y_over_height, dtype=np.float64)
+        self.lib.mvus_ba_points_set.argtypes = [ctypes.c_void_p, ctypes.c_int64, _ip, _dp, _dp]
+        self._check(self.lib.mvus_ba_points_set(self.h, len(cam_slot), _i(cam_slot), _d(frame), _d(yh)))
+        self.G = len(cam_slot)
+
+    def solve_points(self, hs, motion_type, weight, xs0, x0):
+        xs0 = np.ascontiguousarray(xs0, dtype=np.float64)
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        x = np.empty(self.n)
+        r = np.empty(2 * hs.N + self.G)
+        st = BAStats()
+        self.lib.mvus_ba_solve_points.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_double,
+                                                  _dp, _dp, _dp, _dp, ctypes.POINTER(BAStats)]
+        self._check(self.lib.mvus_ba_solve_points(hs.h, self.h, int(motion_type), float(weight), _d(xs0), _d(x0),
+                                                  _d(x), _d(r), ctypes.byref(st)))
+        return x, r, st
+
+    def points_eval(self, hs, motion_type, weight, xs0, x, want_g=True):
+        xs0 = np.ascontiguousarray(xs0, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        r = np.empty(2 * hs.N + self.G)
+        g = np.empty(self.n) if want_g else None
+        cost = ctypes.c_double()
+        self.lib.mvus_ba_points_eval.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_double,
+                                                 _dp, _dp, _dp, _dp, ctypes.POINTER(ctypes.c_double)]
+        self._check(self.lib.mvus_ba_points_eval(hs.h, self.h, int(motion_type), float(weight), _d(xs0), _d(x),
+                                                 _d(r), _d(g), ctypes.byref(cost)))
+        return r, g, cost.value
 
     def normal_equations(self, x, want_dense=True):
         fp = self.fp

@@ -212,9 +212,10 @@ def bundle_adjust(scene, numCam, max_iter=10, rs=False, motion_prior=False, moti
     """Scene.BA(numCam, max_iter, rs, motion_prior, motion_reg, motion_weights, norm, rs_bounds)
     -- reference signature (common.py:441); ``max_iter`` is scipy's max_nfev (common.py:670),
     xtol = 1e-12 as the reference passes, ftol / gtol = scipy defaults."""
-    if motion_prior:
-        raise NotImplementedError('BA(motion_prior=True) (discrete-trajectory mode, common.py:466-467) is '
-                                  'never used by main.py and is not implemented; see SURVEY.md 8b')
+    if motion_prior:                        # discrete-trajectory mode (common.py:466-467 ...): mvus_b200/points.py
+        from . import points
+        return points.bundle_adjust_points(scene, numCam, max_iter=max_iter, rs=rs, motion_weights=motion_weights,
+                                           rs_bounds=rs_bounds, ftol=ftol, xtol=xtol, gtol=gtol)
     assert len(scene.alpha) == scene.numCam and len(scene.beta) == scene.numCam, \
         'The Number of alpha and beta is wrong'
     import time as _time

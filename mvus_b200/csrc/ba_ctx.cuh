@@ -65,6 +65,7 @@ struct DevBuf {
 };
 
 struct NcclApi;   // ba_nccl.cuh
+struct LmHooks;   // mvus_ba.cu: evaluation / accumulation overrides of the LM driver (points mode)
 
 }  // namespace mvus
 
@@ -131,6 +132,13 @@ struct mvus_ba_ctx {
     bool verbose = false;                // MVUS_BA_VERBOSE, read once at mvus_ba_create
     double band_lo = 0.5, band_hi = 1.5; // trust-region band (MVUS_BA_BAND_LO / _HI at create: experiments only)
     int64_t cost_slot = 0;        // index in `partial` where the last evaluation left sum r^2
+
+    // Scene.BA(motion_prior=True) (ba_points.cuh): point meta data on the points handle, LM hooks, dense
+    // cross-camera addend of the reduced camera system
+    int64_t ptG = 0;
+    mvus::DevBuf<int> pt_cam, pt_idx;
+    mvus::DevBuf<double> pt_frame, pt_yH, pt_r, pt_J, Ax;
+    mvus::LmHooks* hooks = nullptr;
 
     // multi-GPU
     int world = 1, rank = 0;

@@ -473,11 +473,11 @@ __global__ void freeze_cols_kernel(double* __restrict__ Ww, int64_t rows, int ld
         if (frozen[cam * Pc + 2]) Ww[row * ldw + cam * Pc + 2] = 0.0;
 }
 
-// S = blockdiag(A) + lam * diag - S~ (lower triangle), rhs = bc - S~[ncP][:]
+// S = blockdiag(A) [+ Ax] + lam * diag - S~ (lower triangle), rhs = bc - S~[ncP][:]
 __global__ void form_schur_kernel(const double* __restrict__ A, const double* __restrict__ bc,
                                   const double* __restrict__ diag_c, double lam, int nc, int Pc, int ldw,
-                                  const int* __restrict__ frozen, double* __restrict__ Sfull,
-                                  double* __restrict__ rhs) {
+                                  const int* __restrict__ frozen, const double* __restrict__ Ax,
+                                  double* __restrict__ Sfull, double* __restrict__ rhs) {
     const int ncP = nc * Pc;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)ncP * ncP) return;
@@ -486,6 +486,7 @@ __global__ void form_schur_kernel(const double* __restrict__ A, const double* __
     double v = -Sfull[(int64_t)row * ldw + col];
     const int cr = row / Pc, cc = col / Pc;
     if (cr == cc) v += A[((int64_t)cr * Pc + (row - cr * Pc)) * Pc + (col - cc * Pc)];
+    else if (Ax) v += Ax[(int64_t)row * ncP + col];          // cross-camera entries (points mode, ba_points.cuh)
     if (row == col) {
         v += lam * diag_c[row];
         rhs[row] = frozen[row] ? 0.0 : bc[row] - Sfull[(int64_t)ncP * ldw + row];
@@ -1177,7 +1178,7 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
         cudaEventRecord(h->evs[2], h->st);
         timed = true;
         form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
-            h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->frozen.p, h->Sd.p, rhs);
+            h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->frozen.p, h->Ax.p, h->Sd.p, rhs);
         h->launches++;
         dense_chol_solve(h, h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
         wdc_kernel<<<(int)((nbq * 32 + 255) / 256), 256, 0, h->st>>>(h->Ww.p, h->dlt_c.p, nbq, ldw, h->dlt_s.p);
@@ -1263,7 +1264,7 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
         e = nccl_sum(h, h->Sd.p, (size_t)ldw * ldw);
         if (e) return e;
         form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
-            h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->frozen.p, h->Sd.p, rhs);
+            h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->frozen.p, h->Ax.p, h->Sd.p, rhs);
         h->launches++;
         dense_chol_solve(h, h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
         e = nccl_bcast0(h, h->dlt_c.p, (size_t)h->ncP);

@@ -19,6 +19,8 @@
 #include "ba_bookkeeping.cuh"
 #include "spl_fit.cuh"
 #include "align.cuh"
+#include "ba_points.cuh"
+#include <functional>
 
 using namespace mvus;
 
@@ -116,12 +118,13 @@ extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
                     &h->x, &h->x_trial, &h->camprep, &h->r, &h->J, &h->mJ, &h->partial, &h->A, &h->D, &h->E,
                     &h->W, &h->Dw, &h->Ew, &h->Ww, &h->ZL, &h->Sd, &h->dlt_c, &h->dlt_s, &h->diag_c,
                     &h->diag_s, &h->gvec, &h->xs, &h->scratch, &h->gt_out, &h->Dt, &h->ZLt, &h->dst, &h->bs, &h->Hb,
-                    &h->Dh, &h->Eh, &h->Wh, &h->ZLh, &h->dsh, &h->DhR, &h->Gh, &h->Linv})
+                    &h->Dh, &h->Eh, &h->Wh, &h->ZLh, &h->dsh, &h->DhR, &h->Gh, &h->Linv,
+                    &h->pt_frame, &h->pt_yH, &h->pt_r, &h->pt_J, &h->Ax})
         b->release(false);
     for (auto* b : {&h->row_off, &h->tile_start, &h->knot_off, &h->ctrl_off, &h->xoff, &h->lut_off}) b->release(false);
     for (auto* b : {&h->tile_cam, &h->tile_cnt, &h->ncoef, &h->deg, &h->lut_n, &h->lut, &h->tau_spl, &h->span,
                     &h->mbase, &h->flag, &h->frozen, &h->chunk_tile0, &h->chunk_nt, &h->chunk_key, &h->chunk_key2,
-                    &h->chunk_id, &h->chunk_perm, &h->k2_queue, &h->touch})
+                    &h->chunk_id, &h->chunk_perm, &h->k2_queue, &h->touch, &h->pt_cam, &h->pt_idx})
         b->release(false);
     h->tau_flag.release(false);
     h->sort_tmp.release(false);
@@ -550,8 +553,16 @@ static int step_scalars(mvus_ba_ctx* h, const double* xd, double out[5]) {
     return MVUS_OK;
 }
 
+// Overrides of the LM driver's two problem-specific steps (points mode, ba_points.cuh): residual (+ Jacobian)
+// evaluation leaving sum r^2 in h->partial[h->cost_slot], and the assembly of the normal equations.
+struct mvus::LmHooks {
+    std::function<int(const double*, bool)> eval;
+    std::function<int()> accum;
+    std::function<int(double*)> copy_r;
+};
+
 static int eval_cost(mvus_ba_ctx* h, const double* xd, bool want_j, double* cost) {
-    int rc = evaluate(h, xd, want_j);
+    int rc = h->hooks ? h->hooks->eval(xd, want_j) : evaluate(h, xd, want_j);
     if (rc) return rc;
     rc = allreduce_cost_slot(h);
     if (rc) return rc;
@@ -628,7 +639,7 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
         if (need_accum) {
             PhaseTimer t(h, 2, &st.ms_accum);
             cudaEventRecord(h->evs[3], h->st);
-            rc = accumulate(h);
+            rc = h->hooks ? h->hooks->accum() : accumulate(h);
             cudaEventRecord(h->evs[4], h->st);
             if (!rc) rc = reduce_normal_equations(h, false);
             cudaEventRecord(h->evs[5], h->st);
@@ -716,7 +727,10 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
         const double ratio = (pred > 0.0 && std::isfinite(Fn)) ? actual / pred : -1.0;
         if (verbose) fprintf(stderr, "[mvus_ba] nfev %d F %.8e Fn %.8e ratio %.3f lam %.3e |d|_D %.3e Delta %.3e |g|inf %.3e\n",
                              st.nfev, F, Fn, ratio, lam, nrm, Delta, st.optimality);
-        if (ratio < 0.25) Delta = 0.25 * nrm;
+        // (a step that INCREASES the cost by more than it promised to decrease it says the model is useless at this
+        //  radius: shrink by 10 like MINPACK's lmder does in that case, not by 4)
+        if (ratio < -1.0) Delta = 0.1 * nrm;
+        else if (ratio < 0.25) Delta = 0.25 * nrm;
         else if (ratio > 0.75 && nrm > 0.7 * Delta) Delta *= 2.0;
         const bool x_small = step_norm < xtol * (xtol + x_norm);
         if (std::isfinite(Fn) && actual > 0.0) {
@@ -758,7 +772,8 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
     st.lambda = lam;
     st.status = status;
     MV_CUDA(h, cudaMemcpyAsync(x_out, h->x.p, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->st));
-    if (r_out) MV_CUDA(h, cudaMemcpyAsync(r_out, h->r.p, h->m * sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    if (r_out && h->hooks) { rc = h->hooks->copy_r(r_out); if (rc) return rc; }
+    else if (r_out) MV_CUDA(h, cudaMemcpyAsync(r_out, h->r.p, h->m * sizeof(double), cudaMemcpyDeviceToHost, h->st));
     MV_CUDA(h, cudaEventRecord(h->ev[7], h->st));
     MV_CUDA(h, cudaEventSynchronize(h->ev[7]));
     float ms = 0.f;
@@ -1031,4 +1046,176 @@ extern "C" int mvus_ba_align(mvus_ba_handle h, const double* x, int64_t n, const
     cleanup();
     if (e != cudaSuccess) return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e));
     return MVUS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Scene.BA(motion_prior=True) (ba_points.cuh)
+extern "C" int mvus_ba_points_set(mvus_ba_handle hp, int64_t G, const int32_t* cam, const double* frame, const double* yH) {
+    if (!hp) return MVUS_ERR_ARG;
+    if (!hp->have_spl) return fail(hp, MVUS_ERR_ARG, "set_splines first (one pseudo-spline with G coefficients)");
+    if (G < 1 || !cam || !frame || !yH) return fail(hp, MVUS_ERR_ARG, "null or empty argument");
+    if (G != hp->n_ctrl) return fail(hp, MVUS_ERR_ARG, "G must equal the number of coefficients of the pseudo-spline");
+    for (int64_t j = 0; j < G; ++j)
+        if (cam[j] < 0 || cam[j] >= hp->nc) return fail(hp, MVUS_ERR_ARG, "camera slot out of range");
+    MV_CUDA(hp, cudaSetDevice(hp->desc.device));
+    MV_CUDA(hp, upload(hp->pt_cam, cam, (size_t)G, hp->st));
+    MV_CUDA(hp, upload(hp->pt_frame, frame, (size_t)G, hp->st));
+    MV_CUDA(hp, upload(hp->pt_yH, yH, (size_t)G, hp->st));
+    MV_CUDA(hp, hp->pt_r.alloc(G));
+    MV_CUDA(hp, hp->pt_J.alloc((size_t)9 * G));
+    MV_CUDA(hp, hp->pt_idx.alloc((size_t)3 * G));
+    MV_CUDA(hp, cudaStreamSynchronize(hp->st));
+    hp->ptG = G;
+    return MVUS_OK;
+}
+
+namespace {
+struct PointsRun {
+    mvus_ba_ctx* hs; mvus_ba_ctx* hp;
+    PointsView pv;
+    int nblk;
+    int check() const {
+        if (!hs || !hp) return MVUS_ERR_ARG;
+        if (!(hs->have_det && hs->have_spl && hp->have_det && hp->have_spl)) return fail(hp, MVUS_ERR_ARG, "both handles need detections and splines set");
+        if (hp->ptG < 1) return fail(hp, MVUS_ERR_ARG, "mvus_ba_points_set first");
+        if (hs->nc != hp->nc || hs->C != hp->C || hs->desc.device != hp->desc.device || hp->N != 0 || hp->M != 0 || hs->M != 0)
+            return fail(hp, MVUS_ERR_ARG, "handles do not describe the same cameras (or the points handle has detections / motion samples)");
+        if (hs->world > 1 || hp->world > 1) return fail(hp, MVUS_ERR_UNSUPPORTED, "the discrete-trajectory mode runs on one GPU");
+        return MVUS_OK;
+    }
+    void init(mvus_ba_ctx* s, mvus_ba_ctx* p, int motion_type, double weight) {
+        hs = s; hp = p;
+        pv = PointsView{p->ptG, p->pt_cam.p, p->pt_frame.p, p->pt_yH.p, p->nc, (int)p->n_other, motion_type, weight,
+                        s->desc.opt_sync, s->desc.opt_rs};
+        nblk = (int)((p->ptG + 127) / 128);
+    }
+    // residuals (and Jacobians) at xd (hp layout); sum r^2 -> hp->partial[hp->cost_slot]
+    int eval(const double* xd, bool want_j) {
+        cudaStreamSynchronize(hp->st);                 // xd was produced on hp's stream; hs works on its own
+        cudaError_t e = cudaMemcpyAsync(hs->x.p, xd, hs->n_other * sizeof(double), cudaMemcpyDeviceToDevice, hs->st);
+        if (e != cudaSuccess) return fail(hp, MVUS_ERR_CUDA, cudaGetErrorString(e));
+        int rc = evaluate(hs, hs->x.p, want_j);
+        if (rc) return fail(hp, rc, hs->err);
+        e = hp->partial.alloc((size_t)nblk + 8);
+        if (e != cudaSuccess) return fail(hp, MVUS_ERR_CUDA, cudaGetErrorString(e));
+        cudaStreamSynchronize(hs->st);
+        if (want_j)
+            points_motion_kernel<true><<<nblk, 128, 0, hp->st>>>(pv, hs->sv, xd, hp->pt_r.p, hp->pt_idx.p, hp->pt_J.p,
+                                                                 hp->partial.p, hp->flag.p);
+        else
+            points_motion_kernel<false><<<nblk, 128, 0, hp->st>>>(pv, hs->sv, xd, hp->pt_r.p, nullptr, nullptr,
+                                                                  hp->partial.p, hp->flag.p);
+        points_cost_kernel<<<1, 256, 0, hp->st>>>(hs->partial.p + hs->cost_slot, hp->partial.p, nblk, hp->partial.p + nblk);
+        hp->cost_slot = nblk;
+        hp->launches += hs->launches + 2;
+        hs->launches = 0;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(hp, MVUS_ERR_CUDA, cudaGetErrorString(e));
+        return MVUS_OK;
+    }
+    int accum() {
+        const size_t qq = (size_t)hp->q * hp->q;
+        const int Pc = hp->Pc, ncP = hp->ncP;
+        double* bc = hp->A.p + (size_t)hp->nc * Pc * Pc;
+        cudaError_t e = hp->Ax.alloc((size_t)ncP * ncP);
+        if (e == cudaSuccess) e = hs->scratch.alloc((size_t)2 * hs->P * std::max<int64_t>(hs->N, 1));
+        if (e != cudaSuccess) return fail(hp, MVUS_ERR_CUDA, cudaGetErrorString(e));
+        cudaMemsetAsync(hp->A.p, 0, hp->A.bytes(), hp->st);
+        cudaMemsetAsync(hp->Ax.p, 0, hp->Ax.bytes(), hp->st);
+        cudaMemsetAsync(hp->D.p, 0, hp->nb * qq * sizeof(double), hp->st);
+        cudaMemsetAsync(hp->E.p, 0, hp->nb * qq * sizeof(double), hp->st);
+        cudaMemsetAsync(hp->Wp(), 0, (size_t)hp->nb * hp->q * hp->ldw * sizeof(double), hp->st);
+        if (hs->N > 0) {
+            deblock_kernel<<<hs->n_tiles, TILE_DET, 0, hp->st>>>(hs->J.p, hs->P, hs->tile_start.p, hs->tile_cnt.p, hs->N,
+                                                              hs->scratch.p, hs->span.p);
+            cam_blocks_kernel<<<dim3(hp->nc, Pc * (Pc + 1)), 256, 0, hp->st>>>(hs->scratch.p, hs->r.p, hs->P, Pc, hs->N,
+                                                                             hs->row_off.p, hp->A.p, bc);
+        }
+        points_accum_kernel<<<nblk, 128, 0, hp->st>>>(pv, hp->x.p, hp->pt_r.p, hp->pt_idx.p, hp->pt_J.p, hp->bw, Pc,
+                                                     hp->ldw, hp->A.p, bc, hp->Ax.p, hp->D.p, hp->E.p, hp->Wp());
+        hp->launches += 3;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(hp, MVUS_ERR_CUDA, cudaGetErrorString(e));
+        return MVUS_OK;
+    }
+    int copy_r(double* r_out) {
+        cudaError_t e = cudaMemcpyAsync(r_out, hs->r.p, 2 * hs->N * sizeof(double), cudaMemcpyDeviceToHost, hp->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(r_out + 2 * hs->N, hp->pt_r.p, hp->ptG * sizeof(double), cudaMemcpyDeviceToHost, hp->st);
+        if (e != cudaSuccess) return fail(hp, MVUS_ERR_CUDA, cudaGetErrorString(e));
+        return MVUS_OK;
+    }
+};
+
+int points_prepare(PointsRun& run, mvus_ba_ctx* hs, mvus_ba_ctx* hp, int32_t motion_type, double weight, const double* xs0) {
+    run.hs = hs; run.hp = hp;
+    int rc = run.check();
+    if (rc) return rc;
+    if (motion_type != MVUS_MOTION_F && motion_type != MVUS_MOTION_KE) return fail(hp, MVUS_ERR_ARG, "motion_type must be F or KE");
+    if (!xs0) return fail(hp, MVUS_ERR_ARG, "null argument");
+    MV_CUDA(hp, cudaSetDevice(hp->desc.device));
+    MV_CUDA(hp, cudaMemcpyAsync(hs->x.p, xs0, hs->n * sizeof(double), cudaMemcpyHostToDevice, hs->st));   // the constant splines
+    MV_CUDA(hp, cudaStreamSynchronize(hs->st));
+    run.init(hs, hp, motion_type, weight);
+    return MVUS_OK;
+}
+}  // namespace
+
+// The mode's residual vector (reference order: reprojection rows of hs, then G motion rows in global_traj order),
+// its gradient J^T r in hp's x layout and the cost, at x.  Diagnostics for the parity tests.
+extern "C" int mvus_ba_points_eval(mvus_ba_handle hs, mvus_ba_handle hp, int32_t motion_type, double motion_weight,
+                                   const double* xs0, const double* x, double* r_out, double* g_out, double* cost) {
+    PointsRun run;
+    int rc = points_prepare(run, hs, hp, motion_type, motion_weight, xs0);
+    if (rc) return rc;
+    if (!x) return fail(hp, MVUS_ERR_ARG, "null argument");
+    rc = ensure_solver(hp);
+    if (rc) return rc;
+    MV_CUDA(hp, cudaMemsetAsync(hp->flag.p, 0, sizeof(int), hp->st));
+    MV_CUDA(hp, cudaMemcpyAsync(hp->x.p, x, hp->n * sizeof(double), cudaMemcpyHostToDevice, hp->st));
+    rc = run.eval(hp->x.p, true);
+    if (rc) return rc;
+    double F = 0.0;
+    rc = read_cost(hp, &F);
+    if (rc) return rc;
+    if (cost) *cost = F;
+    int f = 0;
+    MV_CUDA(hp, cudaMemcpyAsync(&f, hp->flag.p, sizeof(int), cudaMemcpyDeviceToHost, hp->st));
+    MV_CUDA(hp, cudaStreamSynchronize(hp->st));
+    if (f) return fail(hp, MVUS_ERR_UNSUPPORTED, "a motion row spans more than 4 consecutive trajectory points");
+    if (r_out) { rc = run.copy_r(r_out); if (rc) return rc; }
+    if (g_out) {
+        rc = run.accum();
+        if (!rc) rc = compute_diag(hp, true);
+        if (rc) return rc;
+        double* bc = hp->A.p + (size_t)hp->nc * hp->Pc * hp->Pc;
+        gradient_kernel<<<(int)((std::max<int64_t>(hp->n_other, hp->n_ctrl) + 255) / 256), 256, 0, hp->st>>>(
+            bc, hp->bs.p, hp->nc, hp->C, hp->Pc, hp->n_other, hp->sv, hp->n_ctrl, hp->gvec.p);
+        MV_CUDA(hp, cudaMemcpyAsync(g_out, hp->gvec.p, hp->n * sizeof(double), cudaMemcpyDeviceToHost, hp->st));
+    }
+    MV_CUDA(hp, cudaStreamSynchronize(hp->st));
+    return MVUS_OK;
+}
+
+extern "C" int mvus_ba_solve_points(mvus_ba_handle hs, mvus_ba_handle hp, int32_t motion_type, double motion_weight,
+                                    const double* xs0, const double* x0, double* x_out, double* r_out,
+                                    mvus_ba_stats* stats) {
+    PointsRun run;
+    int rc = points_prepare(run, hs, hp, motion_type, motion_weight, xs0);
+    if (rc) return rc;
+    MV_CUDA(hp, cudaMemsetAsync(hp->flag.p, 0, sizeof(int), hp->st));
+    LmHooks hk;
+    hk.eval = [&](const double* xd, bool wj) { return run.eval(xd, wj); };
+    hk.accum = [&]() { return run.accum(); };
+    hk.copy_r = [&](double* r) { return run.copy_r(r); };
+    hp->hooks = &hk;
+    rc = mvus_ba_solve(hp, x0, x_out, r_out, stats);
+    hp->hooks = nullptr;
+    if (rc == MVUS_ERR_UNSUPPORTED) hp->err = "a motion row spans more than 4 consecutive trajectory points";
+    if (!rc) {
+        int f = 0;
+        MV_CUDA(hp, cudaMemcpyAsync(&f, hp->flag.p, sizeof(int), cudaMemcpyDeviceToHost, hp->st));
+        MV_CUDA(hp, cudaStreamSynchronize(hp->st));
+        if (f) return fail(hp, MVUS_ERR_UNSUPPORTED, "a motion row spans more than 4 consecutive trajectory points");
+    }
+    return rc;
 }

@@ -12,12 +12,9 @@ def install(common_module, satellites=True):
 
     def BA(self, numCam, max_iter=10, rs=False, motion_prior=False, motion_reg=False, motion_weights=1,
            norm=False, rs_bounds=False):
-        if motion_prior:                      # discrete-trajectory mode stays on the reference
-            return original(self, numCam, max_iter=max_iter, rs=rs, motion_prior=motion_prior,
-                            motion_reg=motion_reg, motion_weights=motion_weights, norm=norm,
-                            rs_bounds=rs_bounds)
-        return ba.bundle_adjust(self, numCam, max_iter=max_iter, rs=rs, motion_reg=motion_reg,
-                                motion_weights=motion_weights, norm=norm, rs_bounds=rs_bounds)
+        return ba.bundle_adjust(self, numCam, max_iter=max_iter, rs=rs, motion_prior=motion_prior,
+                                motion_reg=motion_reg, motion_weights=motion_weights, norm=norm,
+                                rs_bounds=rs_bounds)
 
     Scene.BA = BA
     Scene._reference_BA = original
