@@ -427,7 +427,8 @@ def main():
                                 'note': 'FP64 mma.sync (DMMA); useful flops = lower triangle n(n+1) x rows; per linear solve'},
               'cyclic_reduction_K3': {'ms': ms_bcr1, 'share_ms': ms[8], 'bound': 'hbm', 'achieved': bcr_bytes / ms_bcr1 / 1e6 if ms_bcr1 else None,
                                       'unit': 'GB/s', 'frac': bcr_bytes / ms_bcr1 / 1e6 / peak if ms_bcr1 else None,
-                                      'bytes_per_launch': bcr_bytes, 'note': 'all elimination levels of one solve; 2 |W~|'},
+                                      'bytes_per_launch': bcr_bytes, 'traffic': traffic.get('cyclic_reduction_K3'),
+                                      'note': 'elimination of W~ in one solve: chunk pre-reduction (chunk_factor + chunk_w) + cyclic reduction of the chunk heads; algorithmic 2 |W~|; traffic = chunk_w_kernel alone'},
               'solve_share_ms': ms[5], 'resjac_share_ms': ms[3], 'accum_share_ms': ms[4], 'reduce_share_ms': ms[9],
               'trial_share_ms': ms[6], 'linear_solves': n_solves}
     kernels = ['resjac_K1', 'accumulate_K2', 'schur_syrk_K3', 'cyclic_reduction_K3']
