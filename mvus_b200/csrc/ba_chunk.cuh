@@ -120,6 +120,121 @@ chunk_factor_kernel(int64_t nb, int Lc, int64_t c_first, double* __restrict__ Dw
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicExch(fail_flag, 1);
 }
 
+// Register / shuffle version of chunk_factor_kernel for Q <= 15 (2Q <= 32 lanes): the shared-memory version above
+// needs ~18 us per block (a dozen __syncwarp-separated phases with shared-memory round trips), and that chain of
+// Lc - 1 dependent blocks is pure latency that neither a bigger problem nor more GPUs hide.  Here
+//   lane i <  Q ("row lane")   holds row i of the current diagonal block (dh) and column i of E_k / ZR_k (m);
+//   lane Q + b ("F lane")      holds column b of the fill-in F_k / ZH_k (m) and column b of the head's block (dh).
+// Cholesky: right-looking, column j's pivot and multipliers travel by shuffles; the triangular solves read
+// L[i][kk] from row lane i; ONE shuffle stream of ZR[kk][a] serves both ZR^T ZR (row lanes -> next diagonal block)
+// and ZR^T ZH (F lanes -> next fill-in), a second one of ZH[kk][a] serves ZH^T ZH (head) and, for the last block,
+// ZH^T ZR (head coupling).  The next block's D and E are prefetched at the top of the iteration.
+template <int Q>
+__global__ void __launch_bounds__(32)
+chunk_factor_fast_kernel(int64_t nb, int Lc, int64_t c_first, double* __restrict__ Dw, double* __restrict__ Ew,
+                         double* __restrict__ ZL, double* __restrict__ Linv, double* __restrict__ Dh,
+                         double* __restrict__ Eh, double* __restrict__ DhR, int* __restrict__ fail_flag) {
+    static_assert(2 * Q <= 32, "one lane per column of [E | F]");
+    constexpr int QQ = Q * Q;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int64_t c = c_first + blockIdx.x;
+    const int64_t j0 = c * Lc, j1 = (j0 + Lc < nb) ? j0 + Lc : nb;
+    if (j0 >= nb) return;
+    if (j1 - j0 == 1) {                                   // a head without followers keeps its original coupling
+        for (int i = lane; i < QQ; i += 32) {
+            Dh[c * QQ + i] = Dw[j0 * QQ + i];
+            Eh[c * QQ + i] = (j1 < nb) ? Ew[j0 * QQ + i] : 0.0;
+            if (j1 < nb) DhR[(c + 1) * QQ + i] = 0.0;
+        }
+        return;
+    }
+    const bool isrow = lane < Q, isf = lane >= Q && lane < 2 * Q;
+    const int li = isrow ? lane : 0, lb = isf ? lane - Q : 0;
+    double m[Q], dh[Q], nxt[Q], rn[Q];
+    double rinv = 1.0;                                    // row lane i: 1 / L[i][i] of the current block
+    bool bad = false;
+#pragma unroll
+    for (int a = 0; a < Q; ++a) {
+        // row lanes: row li of D_{j0+1}, column li of E_{j0+1}; F lanes: column lb of E_{j0}^T and of the head's block
+        dh[a] = isrow ? Dw[(j0 + 1) * QQ + li * Q + a] : Dw[j0 * QQ + a * Q + lb];
+        m[a] = isrow ? ((j0 + 2 < nb) ? Ew[(j0 + 1) * QQ + a * Q + li] : 0.0) : Ew[j0 * QQ + lb * Q + a];
+    }
+    for (int64_t k = j0 + 1; k < j1; ++k) {
+        const bool more = k + 1 < j1, has_r = k + 1 < nb;
+        // prefetch block k + 1 (row lanes): its diagonal block row and its coupling column
+#pragma unroll
+        for (int a = 0; a < Q; ++a) {
+            nxt[a] = (more && isrow) ? Dw[(k + 1) * QQ + li * Q + a] : 0.0;
+            rn[a] = (more && isrow && k + 2 < nb) ? Ew[(k + 1) * QQ + a * Q + li] : 0.0;
+        }
+        // Cholesky of the diagonal block (rows in the row lanes)
+#pragma unroll
+        for (int j = 0; j < Q; ++j) {
+            double djj = __shfl_sync(FULL, dh[j], j);
+            if (!(djj > 0.0)) { bad = true; djj = 1.0; }
+            const double inv = 1.0 / sqrt(djj);
+            if (lane == j) rinv = inv;
+            const double lij = dh[j] * inv;                // row lane i >= j: L[i][j]
+            if (isrow) dh[j] = lij;
+#pragma unroll
+            for (int k2 = j + 1; k2 < Q; ++k2) {
+                const double lkj = __shfl_sync(FULL, lij, k2);
+                if (isrow) dh[k2] -= lij * lkj;            // entry (i, k2); meaningful for k2 <= i
+            }
+        }
+        // ZR = L^-1 E, ZH = L^-1 F: every lane solves its column
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            double v = m[i];
+#pragma unroll
+            for (int kk = 0; kk < i; ++kk) v -= __shfl_sync(FULL, dh[kk], i) * m[kk];
+            m[i] = v * __shfl_sync(FULL, rinv, i);
+        }
+        // store L (rows), 1/diag, ZR (row lanes' columns), ZH (F lanes' columns)
+#pragma unroll
+        for (int a = 0; a < Q; ++a) {
+            if (isrow) { Dw[k * QQ + li * Q + a] = dh[a]; Ew[k * QQ + a * Q + li] = m[a]; }
+            if (isf) ZL[k * QQ + a * Q + lb] = m[a];
+        }
+        if (isrow) Linv[k * Q + li] = rinv;
+        // nxt -= ZR[:, a] . own column: row lanes -> D_{k+1} - ZR^T ZR, F lanes -> -ZR^T ZH = next fill-in
+#pragma unroll
+        for (int kk = 0; kk < Q; ++kk)
+#pragma unroll
+            for (int a = 0; a < Q; ++a) nxt[a] -= __shfl_sync(FULL, m[kk], a) * m[kk];
+        if (!more && has_r && isrow) {
+#pragma unroll
+            for (int a = 0; a < Q; ++a) DhR[(c + 1) * QQ + li * Q + a] = -nxt[a];       // (ZR^T ZR)[li][a]
+        }
+        // head: Hd[:, b] -= ZH[:, a] . ZH[:, b] (F lanes).  In the last block the row lanes collect -ZH^T ZR
+        // (the head coupling) from the same shuffle stream, in rn (no next block to prefetch then)
+#pragma unroll
+        for (int kk = 0; kk < Q; ++kk)
+#pragma unroll
+            for (int a = 0; a < Q; ++a) {
+                const double bf = __shfl_sync(FULL, m[kk], Q + a) * m[kk];
+                dh[a] -= isf ? bf : 0.0;
+                rn[a] -= (isrow && !more) ? bf : 0.0;
+            }
+        if (more) {
+#pragma unroll
+            for (int a = 0; a < Q; ++a) {
+                if (isrow) dh[a] = nxt[a];
+                m[a] = isrow ? rn[a] : nxt[a];
+            }
+        } else if (isrow) {
+#pragma unroll
+            for (int a = 0; a < Q; ++a) Eh[c * QQ + a * Q + li] = has_r ? rn[a] : 0.0;  // (-ZH^T ZR)[a][li]
+        }
+    }
+    if (isf) {
+#pragma unroll
+        for (int a = 0; a < Q; ++a) Dh[c * QQ + a * Q + lb] = dh[a];
+    }
+    if (bad && lane == 0) atomicExch(fail_flag, 1);
+}
+
 // ---- W~ part: one thread per column streams down the chunk --------------------------------
 // grid (chunks, column groups of CW_T), block CW_T.  Wsrc: where a block's original rows are read (may be Ww
 // itself: every element is read before the same thread overwrites it).  Writes W~_k into Ww (zero rows for

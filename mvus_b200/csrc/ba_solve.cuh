@@ -1100,15 +1100,15 @@ inline void prereduce_range(mvus_ba_ctx* h, int64_t lo, int64_t hi, const double
     // the kernels see the blocks [0, nbv): a block couples to its right neighbour iff that neighbour exists
     const int64_t nbv = (hi < h->nb) ? hi + 1 : h->nb;
     const dim3 gw(nchunk, (ldw + CW_T - 1) / CW_T);
-#define MV_CHUNK(QQ)                                                                                              \
-    chunk_factor_kernel<QQ><<<nchunk, 32, 0, h->st>>>(nbv, Lc, c0, h->Dw.p, h->Ew.p, h->ZL.p, h->Linv.p, h->Dh.p, h->Eh.p, \
-                                                      h->DhR.p, fail_flag);                                       \
+#define MV_CHUNK(QQ, FACTOR)                                                                                       \
+    FACTOR<QQ><<<nchunk, 32, 0, h->st>>>(nbv, Lc, c0, h->Dw.p, h->Ew.p, h->ZL.p, h->Linv.p, h->Dh.p, h->Eh.p,        \
+                                         h->DhR.p, fail_flag);                                                    \
     chunk_w_kernel<QQ><<<gw, CW_T, 0, h->st>>>(nbv, Lc, c0, ldw, wsrc, h->Dw.p, h->Ew.p, h->ZL.p, h->Linv.p, h->Ww.p, h->Wh.p, h->Gh.p)
     switch (q) {
-        case 9: MV_CHUNK(9); break;
-        case 12: MV_CHUNK(12); break;
-        case 15: MV_CHUNK(15); break;
-        default: MV_CHUNK(18); break;
+        case 9: MV_CHUNK(9, chunk_factor_fast_kernel); break;
+        case 12: MV_CHUNK(12, chunk_factor_fast_kernel); break;
+        case 15: MV_CHUNK(15, chunk_factor_fast_kernel); break;
+        default: MV_CHUNK(18, chunk_factor_kernel); break;
     }
 #undef MV_CHUNK
     head_fix_kernel<<<(int)(c1 - c0 + (has_next ? 1 : 0)), 256, 0, h->st>>>(c0, q, ldw, h->Dh.p, h->DhR.p, h->Wh.p, h->Gh.p);
