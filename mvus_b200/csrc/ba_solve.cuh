@@ -496,44 +496,48 @@ __global__ void form_schur_kernel(const double* __restrict__ A, const double* __
 }
 
 // Dense Cholesky + solve of the reduced camera system (n = nc*Pc <= 1152): right-looking blocked
-// factorisation, panel width 32, three small kernels per panel (diagonal block on one CTA,
-// panel solve and trailing update spread over the grid), then a blocked forward/backward
-// substitution on one CTA.  Lower triangle, leading dimension lds, in place.
+// factorisation, panel width 32.  Lower triangle, leading dimension lds >= n + 1, in place.
 constexpr int CH_B = 32;
-__global__ void __launch_bounds__(CH_B * CH_B)
-chol_diag_kernel(double* __restrict__ S, int lds, int n, int p0, int* __restrict__ fail_flag) {
+// Panel step of the right-looking Cholesky, two launches per 32-wide panel (round 1 used three plus a
+// forward/backward solve on one warp: 55 dependent launches, 1.3 ms at n = 576, replicated on every rank):
+//   chol_panel_kernel   EVERY CTA factors the 32 x 32 diagonal block itself in shared memory (redundant, but
+//                       it removes a dependent launch; CTA 0 writes L_pp back) and then solves its 32 rows below
+//                       the panel, X L_pp^T = S_ip;
+//   chol_update_kernel  trailing update S_ij -= L_ip L_jp^T.
+// The right-hand side rides along as ROW n of S: after the last panel it holds y = L^-1 rhs (the forward
+// substitution), so only the backward substitution is left for chol_back_kernel.
+__global__ void __launch_bounds__(256)
+chol_panel_kernel(double* __restrict__ S, int lds, int n, int p0, int* __restrict__ fail_flag) {
     __shared__ double L[CH_B][CH_B + 1];
-    const int r = threadIdx.y, c = threadIdx.x;
-    const int nb = min(CH_B, n - p0);
-    L[r][c] = (r < nb && c < nb && c <= r) ? S[(int64_t)(p0 + r) * lds + p0 + c] : (r == c ? 1.0 : 0.0);
+    const int nb = min(CH_B, n - p0), tid = threadIdx.x;
+    for (int i = tid; i < CH_B * CH_B; i += 256) {
+        const int r = i / CH_B, c = i - r * CH_B;
+        L[r][c] = (r < nb && c <= r) ? S[(int64_t)(p0 + r) * lds + p0 + c] : (r == c ? 1.0 : 0.0);
+    }
     __syncthreads();
     for (int j = 0; j < nb; ++j) {
-        if (r == j && c == j) {
-            double d = L[j][j];
-            if (!(d > 0.0)) { atomicExch(fail_flag, 1); d = 1.0; }
-            L[j][j] = sqrt(d);
+        double d = L[j][j];
+        const bool bad = !(d > 0.0);
+        d = sqrt(bad ? 1.0 : d);
+        if (bad && tid == 0 && blockIdx.x == 0) atomicExch(fail_flag, 1);
+        __syncthreads();
+        if (tid == 0) L[j][j] = d;
+        if (tid > j && tid < nb) L[tid][j] /= d;
+        __syncthreads();
+        for (int e = tid; e < CH_B * CH_B; e += 256) {
+            const int r = e / CH_B, c = e - r * CH_B;
+            if (c > j && c <= r && r < nb) L[r][c] -= L[r][j] * L[c][j];
         }
         __syncthreads();
-        if (c == j && r > j) L[r][j] /= L[j][j];
-        __syncthreads();
-        if (c > j && c <= r) L[r][c] -= L[r][j] * L[c][j];
-        __syncthreads();
     }
-    if (r < nb && c < nb && c <= r) S[(int64_t)(p0 + r) * lds + p0 + c] = L[r][c];
-}
-
-// rows below the panel: X L_pp^T = S_ip  ->  one warp per row block of 32 rows, thread = row
-__global__ void __launch_bounds__(CH_B)
-chol_panel_kernel(double* __restrict__ S, int lds, int n, int p0) {
-    __shared__ double L[CH_B][CH_B + 1];
-    const int nb = min(CH_B, n - p0);
-    for (int i = threadIdx.x; i < CH_B * CH_B; i += CH_B) {
-        const int r = i / CH_B, c = i - r * CH_B;
-        L[r][c] = (r < nb && c <= r) ? S[(int64_t)(p0 + r) * lds + p0 + c] : 0.0;
-    }
-    __syncthreads();
-    const int row = p0 + nb + blockIdx.x * CH_B + threadIdx.x;
-    if (row >= n) return;
+    if (blockIdx.x == 0)
+        for (int i = tid; i < CH_B * CH_B; i += 256) {
+            const int r = i / CH_B, c = i - r * CH_B;
+            if (r < nb && c <= r) S[(int64_t)(p0 + r) * lds + p0 + c] = L[r][c];
+        }
+    // rows below the panel, the right-hand-side row n included: thread = row
+    const int row = p0 + nb + blockIdx.x * CH_B + tid;
+    if (tid >= CH_B || row > n) return;
     double x[CH_B];
     double* sr = S + (int64_t)row * lds + p0;
 #pragma unroll
@@ -551,7 +555,7 @@ chol_panel_kernel(double* __restrict__ S, int lds, int n, int p0) {
     for (int c = 0; c < CH_B; ++c) if (c < nb) sr[c] = x[c];
 }
 
-// trailing update S_ij -= L_ip L_jp^T for 32x32 tiles i >= j below the panel
+// trailing update S_ij -= L_ip L_jp^T for 32x32 tiles i >= j below the panel (rows up to and including n)
 __global__ void __launch_bounds__(CH_B * 8)
 chol_update_kernel(double* __restrict__ S, int lds, int n, int p0) {
     __shared__ double Li[CH_B][CH_B + 1], Lj[CH_B][CH_B + 1];
@@ -562,7 +566,7 @@ chol_update_kernel(double* __restrict__ S, int lds, int n, int p0) {
     const int i0 = p0 + nb + ti * CH_B, j0 = p0 + nb + tj * CH_B;
     for (int i = threadIdx.x; i < CH_B * CH_B; i += blockDim.x) {
         const int r = i / CH_B, c = i - r * CH_B;
-        Li[r][c] = (i0 + r < n && c < nb) ? S[(int64_t)(i0 + r) * lds + p0 + c] : 0.0;
+        Li[r][c] = (i0 + r <= n && c < nb) ? S[(int64_t)(i0 + r) * lds + p0 + c] : 0.0;
         Lj[r][c] = (j0 + r < n && c < nb) ? S[(int64_t)(j0 + r) * lds + p0 + c] : 0.0;
     }
     __syncthreads();
@@ -571,7 +575,7 @@ chol_update_kernel(double* __restrict__ S, int lds, int n, int p0) {
     for (int k = 0; k < 4; ++k) {
         const int r = rq * 4 + k;
         const int gi = i0 + r, gj = j0 + c;
-        if (gi < n && gj < n && gj <= gi) {
+        if (gi <= n && gj < n && gj <= gi) {
             double acc = 0.0;
 #pragma unroll
             for (int kk = 0; kk < CH_B; ++kk) acc += Li[r][kk] * Lj[c][kk];
@@ -580,42 +584,28 @@ chol_update_kernel(double* __restrict__ S, int lds, int n, int p0) {
     }
 }
 
-// x = (L L^T)^-1 rhs, blocked by 32, one CTA of 1024 threads
+// x = L^-T y with y = row n of S; blocked by 32 on one CTA, the diagonal block of every step staged in shared
+// memory first (the 32 dependent steps then run on shared memory instead of 32 global round trips)
 __global__ void __launch_bounds__(1024)
-chol_solve_kernel(const double* __restrict__ S, int lds, int n, double* __restrict__ rhs,
-                  double* __restrict__ xout) {
+chol_back_kernel(const double* __restrict__ S, int lds, int n, double* __restrict__ xout) {
     __shared__ double y[1152];
+    __shared__ double Ld[CH_B][CH_B + 1];
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < n; i += nt) y[i] = rhs[i];
+    for (int i = tid; i < n; i += nt) y[i] = S[(int64_t)n * lds + i];
     __syncthreads();
-    for (int p0 = 0; p0 < n; p0 += CH_B) {            // forward
+    for (int p0 = ((n - 1) / CH_B) * CH_B; p0 >= 0; p0 -= CH_B) {
         const int nb = min(CH_B, n - p0);
-        if (tid < 32) {
-            for (int j = 0; j < nb; ++j) {
-                const double yj = y[p0 + j] / S[(int64_t)(p0 + j) * lds + p0 + j];
-                __syncwarp();
-                if (tid == 0) y[p0 + j] = yj;
-                if (tid > j && tid < nb) y[p0 + tid] -= S[(int64_t)(p0 + tid) * lds + p0 + j] * yj;
-                __syncwarp();
-            }
+        {
+            const int r = tid / CH_B, c = tid - r * CH_B;      // 1024 threads = one 32 x 32 block
+            Ld[r][c] = (r < nb && c <= r) ? S[(int64_t)(p0 + r) * lds + p0 + c] : 0.0;
         }
         __syncthreads();
-        for (int i = p0 + nb + tid; i < n; i += nt) {
-            const double* sr = S + (int64_t)i * lds + p0;
-            double acc = 0.0;
-            for (int k = 0; k < nb; ++k) acc += sr[k] * y[p0 + k];
-            y[i] -= acc;
-        }
-        __syncthreads();
-    }
-    for (int p0 = ((n - 1) / CH_B) * CH_B; p0 >= 0; p0 -= CH_B) {     // backward
-        const int nb = min(CH_B, n - p0);
         if (tid < 32) {
             for (int j = nb - 1; j >= 0; --j) {
-                const double xj = y[p0 + j] / S[(int64_t)(p0 + j) * lds + p0 + j];
+                const double xj = y[p0 + j] / Ld[j][j];
                 __syncwarp();
                 if (tid == 0) y[p0 + j] = xj;
-                if (tid < j) y[p0 + tid] -= S[(int64_t)(p0 + j) * lds + p0 + tid] * xj;
+                if (tid < j) y[p0 + tid] -= Ld[j][tid] * xj;
                 __syncwarp();
             }
         }
@@ -631,19 +621,19 @@ chol_solve_kernel(const double* __restrict__ S, int lds, int n, double* __restri
 }
 
 inline void dense_chol_solve(mvus_ba_ctx* h, double* S, int lds, int n, double* rhs, double* xout, int* fail_flag) {
+    cudaMemcpyAsync(S + (int64_t)n * lds, rhs, n * sizeof(double), cudaMemcpyDeviceToDevice, h->st);   // rhs = row n
     for (int p0 = 0; p0 < n; p0 += CH_B) {
         const int nb = std::min(CH_B, n - p0);
-        chol_diag_kernel<<<1, dim3(CH_B, CH_B), 0, h->st>>>(S, lds, n, p0, fail_flag);
+        const int rem = n + 1 - p0 - nb;                   // rows below the panel, rhs row included (>= 1)
+        const int nblk = (rem + CH_B - 1) / CH_B;
+        chol_panel_kernel<<<nblk, 256, 0, h->st>>>(S, lds, n, p0, fail_flag);
         h->launches++;
-        const int rem = n - p0 - nb;
-        if (rem > 0) {
-            const int nblk = (rem + CH_B - 1) / CH_B;
-            chol_panel_kernel<<<nblk, CH_B, 0, h->st>>>(S, lds, n, p0);
+        if (n - p0 - nb > 0) {
             chol_update_kernel<<<nblk * (nblk + 1) / 2, CH_B * 8, 0, h->st>>>(S, lds, n, p0);
-            h->launches += 2;
+            h->launches++;
         }
     }
-    chol_solve_kernel<<<1, 1024, 0, h->st>>>(S, lds, n, rhs, xout);
+    chol_back_kernel<<<1, 1024, 0, h->st>>>(S, lds, n, xout);
     h->launches++;
 }
 
