@@ -117,7 +117,7 @@ def fit_spline(t0, t1, n_coef, fps_ref=30.0):
 def make_flight(nc=4, det_per_cam=1500, frames_per_knot=15.0, seed=0, noise=0.5,
                 rolling_shutter=False, distortion=True, opt_calib=False, motion_type=None,
                 motion_weights=1e4, gaps=(), perturb=1.0, n_coef=None, uncovered=0.02,
-                init_rs=None):
+                init_rs=None, rho_true=None):
     """Build a BA-ready Scene: ground truth + perturbation (pose 1 deg / 0.2 m, beta +-2
     frames, alpha +-min(1e-4, 2/T), rho +-0.1, control points +-0.05 m),
     scaled by ``perturb``.
@@ -227,6 +227,8 @@ def write_dataset(out_dir, nc=4, det_per_cam=5000, seed=0, noise=0.5, rolling_sh
     cf[1:] = np.round(rng_f.uniform(-60, 60, nc - 1))
     beta = cf[0] - alpha * cf
     rho = rng_f.uniform(0.1, 0.8, nc) if rolling_shutter else np.zeros(nc)
+    if rho_true is not None:                      # (tests: read-out speeds outside [0, 1] make the rs bounds active)
+        rho = np.asarray(rho_true, dtype=np.float64).copy()
     det_paths, cam_paths = [], []
     for i, cam in enumerate(cams):
         f0 = int(np.ceil((0.0 - beta[i]) / alpha[i]))
