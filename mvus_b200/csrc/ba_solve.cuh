@@ -270,8 +270,8 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, int odd_o
 // 8-byte banks per half warp) with ONE __syncthreads per chunk; rows of W~ are 8-byte aligned only
 // (ldw = ncP + 1 is odd), hence 8-byte copies, zero-filled past the slab / the last column.
 // Split-K over row slabs, partial tiles reduced with FP64 RED.  Only the ncP camera columns enter
-// the GEMM: the right-hand-side column (W~^T w_rhs, one row of S~) is a GEMV (wtw_rhs_kernel), so
-// that 576 = 18 x 32 columns need no padding strip.
+// the GEMM (576 = 18 x 32 columns need no padding strip): the right-hand-side column (W~^T w_rhs, one row
+// of S~) is accumulated on the scalar FP64 pipe by an otherwise idle warp of the diagonal tile pairs.
 // History: v1 4x4 scalar micro-tiles 4.4 TFLOP/s, v2 8x8 scalar 6.2 TFLOP/s, v3 FP64 MMA with a
 // single-buffered register-prefetch pipeline 23 TFLOP/s issued (DMMA pipe 60 %; profiles/r1_notes.md).
 constexpr int SY_T = 128, SY_K = 32, SY_LD = SY_T + 4, SY_STAGES = 3, SY_NQ = SY_K / 4;
@@ -323,6 +323,11 @@ syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, 
     // warp tiles that only hold padding columns (last tile) or lie strictly above the diagonal of a
     // diagonal tile pair contribute nothing: they still help staging, but skip the MMAs
     const bool warp_active = (ti * SY_T + wy * 32 < n) && (tj * SY_T + wx * 32 < n) && !(diag && wx > wy);
+    // The right-hand-side row of S~ (W~^T w_rhs) is accumulated by one of the six warps a diagonal tile pair leaves
+    // idle: the five diagonal pairs cover every column once per row slab, the data are in shared memory anyway,
+    // and the separate GEMV pass over W~ (0.45 ms, 2.8 GB at config 4) is gone.
+    const bool rhs_warp = diag && warp == 15;
+    double racc[4] = {0.0, 0.0, 0.0, 0.0};
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(sy_smem);
     // Staging: each thread copies 4 elements of each panel per chunk -- column cc = tid & 127 of the rows
     // kq, kq + 4, kq + 8, kq + 12 (kq = tid >> 7).  Everything that does not change from chunk to chunk is
@@ -360,6 +365,14 @@ syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, 
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa), "l"(inr ? pa + k * ld4 : Ww), "r"(inr ? sza : 0u) : "memory");
             if (!diag)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sa + PANEL_B), "l"(inr ? pb + k * ld4 : Ww), "r"(inr ? szb : 0u) : "memory");
+            else if (k == 0 && tid < SY_K) {
+                // diagonal tile pairs do not use the B panel: its first SY_K slots take the right-hand-side column
+                // W~[row][n] of the chunk's rows for the fused rhs row (see the rhs warp below)
+                const int64_t row = r0 + (int64_t)c * SY_K + tid;
+                const bool rin = row < r1;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(sbase + (unsigned)st * STAGE_B + PANEL_B + (unsigned)tid * 8u),
+                             "l"(rin ? Ww + row * ldw + n : Ww), "r"(rin ? 8u : 0u) : "memory");
+            }
             if (k == SY_NQ - 1) {
                 pa += ld16; pb += ld16;
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(bar0 + 8u * st) : "memory");
@@ -389,6 +402,15 @@ syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, 
         k2_mbar_wait(bar0 + 8u * st, (unsigned)((c / SY_STAGES) & 1));        // chunk c has landed
         const double* As = sy_smem + (size_t)st * 2 * SY_K * SY_LD;
         const double* Bp = diag ? As : As + SY_K * SY_LD;
+        if (rhs_warp) {                        // S~[n][ti*128 + col] += W~[row][n] * W~[row][col] on the scalar FP64 pipe
+            const double* rv = As + SY_K * SY_LD;
+#pragma unroll 8
+            for (int row = 0; row < SY_K; ++row) {
+                const double g = rv[row];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) racc[k] += g * As[row * SY_LD + lane + 32 * k];
+            }
+        }
         // each quarter of the chunk's MMAs is queued BEFORE a quarter of the copies of chunk c + STAGES - 1 is
         // issued, so the FP64-MMA pipe has work while this warp runs through its staging instructions
 #pragma unroll
@@ -399,6 +421,13 @@ syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, 
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar0 + 8u * (SY_STAGES + st)) : "memory");
             }
             issue_q(c + SY_STAGES - 1, k);
+        }
+    }
+    if (rhs_warp) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int col = ti * SY_T + lane + 32 * k;
+            if (col < n && racc[k] != 0.0) atomicAdd(Sfull + (int64_t)n * ldw + col, racc[k]);
         }
     }
 #pragma unroll
@@ -412,41 +441,6 @@ syrk_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, 
                 const double v = acc[i][j][e];
                 if (row < n && col <= row && v != 0.0) atomicAdd(Sfull + (int64_t)row * ldw + col, v);
             }
-}
-
-// S~[n][0..n) = sum over rows of W~[row][n] * W~[row][0..n): the right-hand-side row of the Schur system.
-// One CTA per slab of rows; thread -> columns tid + 256 k (a row is read with unit stride by the CTA), four rows
-// in flight per thread; split-K reduced with FP64 RED.  HBM-bound: one pass over W~.
-constexpr int RHS_T = 256, RHS_NC = (1152 + RHS_T - 1) / RHS_T;
-__global__ void __launch_bounds__(RHS_T)
-wtw_rhs_kernel(const double* __restrict__ Ww, int64_t R, int ldw, int n, int slab, double* __restrict__ Sfull) {
-    const int64_t r0 = (int64_t)blockIdx.x * slab, r1 = r0 + slab < R ? r0 + slab : R;
-    double acc[RHS_NC];
-#pragma unroll
-    for (int k = 0; k < RHS_NC; ++k) acc[k] = 0.0;
-    for (int64_t row = r0; row < r1; row += 4) {
-        double g[4], v[4][RHS_NC];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const bool in = row + u < r1;
-            const double* wr = Ww + (row + u) * ldw;
-            g[u] = in ? __ldg(wr + n) : 0.0;
-#pragma unroll
-            for (int k = 0; k < RHS_NC; ++k) {
-                const int c = threadIdx.x + RHS_T * k;
-                v[u][k] = (in && c < n) ? __ldcs(wr + c) : 0.0;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int k = 0; k < RHS_NC; ++k) acc[k] += g[u] * v[u][k];
-    }
-#pragma unroll
-    for (int k = 0; k < RHS_NC; ++k) {
-        const int c = threadIdx.x + RHS_T * k;
-        if (c < n && acc[k] != 0.0) atomicAdd(Sfull + (int64_t)n * ldw + c, acc[k]);
-    }
 }
 
 // rs_bounds (common.py:655-660, scipy trf_bounds): active-set treatment of the box 0 <= rho <= 1.
@@ -1028,9 +1022,7 @@ inline void launch_syrk(mvus_ba_ctx* h, const double* Wrows, int64_t R, double* 
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM); attr_set = true; }
     syrk_kernel<<<g, 512, SY_SMEM, h->st>>>(Wrows, R, ldw, n, slab, (int)nbig, small, Sfull);
-    const int rslab = 128;                                 // rows per CTA of the right-hand-side GEMV
-    wtw_rhs_kernel<<<(int)((R + rslab - 1) / rslab), RHS_T, 0, h->st>>>(Wrows, R, ldw, n, rslab, Sfull);
-    h->launches += 2;
+    h->launches += 1;
 }
 
 // copy the chunk-head blocks of this rank (and its ghost) into the compact top-level arrays
