@@ -64,6 +64,12 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// Page-locked scratch for the scalars a handle reads back (costs, step norms): cudaMallocHost / cudaFreeHost take
+// milliseconds and serialise every thread of the process on the driver, which dominated the life of a small
+// problem's handle (22 of 36 ms per 7 x 5000 problem: tests/cfg5_probe.py); blocks are recycled instead.
+double* pin_scratch_acquire();               // mvus_ba.cu: 64 doubles
+void pin_scratch_release(double* p);
+
 struct NcclApi;   // ba_nccl.cuh
 struct LmHooks;   // mvus_ba.cu: evaluation / accumulation overrides of the LM driver (points mode)
 

@@ -101,18 +101,41 @@ extern "C" int mvus_ba_create(const mvus_ba_desc* desc, mvus_ba_handle* out) {
         for (int k = 0; k < 8 && e == cudaSuccess; ++k) e = cudaEventCreate(&h->ev[k]);
         for (int k = 0; k < 6 && e == cudaSuccess; ++k) e = cudaEventCreate(&h->evs[k]);
     }
-    if (e == cudaSuccess) { h->h_pin_n = 64; e = cudaMallocHost((void**)&h->h_pin, h->h_pin_n * sizeof(double)); }
+    if (e == cudaSuccess) { h->h_pin_n = 64; h->h_pin = pin_scratch_acquire(); if (!h->h_pin) e = cudaErrorMemoryAllocation; }
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, desc->device);
     if (e != cudaSuccess) { g_create_err = cudaGetErrorString(e); delete h; return MVUS_ERR_CUDA; }
     *out = h;
     return MVUS_OK;
 }
 
+namespace {
+std::mutex g_pin_mu;
+std::vector<double*> g_pin_free;
+}
+double* mvus::pin_scratch_acquire() {
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        if (!g_pin_free.empty()) { double* p = g_pin_free.back(); g_pin_free.pop_back(); return p; }
+    }
+    double* p = nullptr;
+    if (cudaMallocHost((void**)&p, 64 * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void mvus::pin_scratch_release(double* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pin_free.push_back(p);
+}
+
 extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
     if (!h) return;
     cudaSetDevice(h->desc.device);
     nccl_destroy(h);
-    cudaDeviceSynchronize();                          // once; the buffers are then released without further syncs
+    // everything that used this handle's buffers ran on its own stream (uploads and the points mode join it before
+    // they return), so waiting for that stream -- not for the whole device, which would stall every other handle
+    // of the process -- is enough before the buffers go back to the pool
+    if (h->st) cudaStreamSynchronize(h->st);
+    cudaStreamSynchronize(cudaStreamPerThread);
     for (auto* b : {&h->frame, &h->xr, &h->yr, &h->obs_u, &h->obs_v, &h->calib, &h->height, &h->int_a,
                     &h->int_b, &h->knots, &h->spanpoly, &h->span_t0, &h->lut_t0, &h->lut_invh, &h->tau,
                     &h->x, &h->x_trial, &h->camprep, &h->r, &h->J, &h->mJ, &h->partial, &h->A, &h->D, &h->E,
@@ -128,7 +151,7 @@ extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
         b->release(false);
     h->tau_flag.release(false);
     h->sort_tmp.release(false);
-    if (h->h_pin) cudaFreeHost(h->h_pin);
+    pin_scratch_release(h->h_pin);
     for (int k = 0; k < 8; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     for (int k = 0; k < 6; ++k) if (h->evs[k]) cudaEventDestroy(h->evs[k]);
     if (h->st) cudaStreamDestroy(h->st);
@@ -215,9 +238,10 @@ static cudaError_t upload_segments(int device, const std::vector<UploadSeg>& seg
 // world size at the first solve.  Any later mvus_ba_set_detections / set_splines / comm_init must
 // make solver_alloc run again, or K2 and the cyclic-reduction levels would use stale block counts.
 void mvus::invalidate_solver(mvus_ba_ctx* h) {
-    h->A.release();
-    h->W.release();
-    h->J.release();
+    if (h->st) cudaStreamSynchronize(h->st);      // (the handle's own stream is the only user of these)
+    h->A.release(false);
+    h->W.release(false);
+    h->J.release(false);
 }
 
 static int finish_dims(mvus_ba_ctx* h) {
@@ -894,7 +918,7 @@ extern "C" int mvus_ba_global_traj(mvus_ba_handle h, const double* x, const int3
     if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, tb2, flag.p, pos.p, (int)N, h->st);
     size_t tb = tb1 > tb2 ? tb1 : tb2;
     if (e == cudaSuccess) e = tmp.alloc(tb);
-    auto cleanup = [&]() { ts.release(); ts_s.release(); idx.release(); idx_s.release(); flag.release(); pos.release(); cams.release(); tmp.release(); };
+    auto cleanup = [&]() { cudaStreamSynchronize(h->st); ts.release(false); ts_s.release(false); idx.release(false); idx_s.release(false); flag.release(false); pos.release(false); cams.release(false); tmp.release(false); };
     if (e != cudaSuccess) { cleanup(); return fail(h, MVUS_ERR_CUDA, cudaGetErrorString(e)); }
     if (gd_out) {          // global_detections: 3 x N (camera id, frame id, time stamp), concatenation order
         e = h->scratch.alloc((size_t)3 * N);
@@ -979,7 +1003,7 @@ extern "C" int mvus_ba_spline_to_traj(mvus_ba_handle h, const double* x, const d
     DevBuf<double> xd, td, od;
     DevBuf<int> flag, pos;
     DevBuf<unsigned char> tmp;
-    auto cleanup = [&]() { xd.release(); td.release(); od.release(); flag.release(); pos.release(); tmp.release(); };
+    auto cleanup = [&]() { cudaStreamSynchronize(h->st); xd.release(false); td.release(false); od.release(false); flag.release(false); pos.release(false); tmp.release(false); };
     cudaError_t e = upload(xd, x, (size_t)nx, h->st);
     if (e == cudaSuccess) e = upload(td, t, (size_t)n, h->st);
     if (e == cudaSuccess) e = flag.alloc(n);
@@ -1024,7 +1048,7 @@ extern "C" int mvus_ba_align(mvus_ba_handle h, const double* x, int64_t n, const
     const int64_t nx = h->n_other + 3 * h->n_ctrl;
     DevBuf<double> xd, td, pd, sd, me, Md, ed;
     DevBuf<int64_t> cd;
-    auto cleanup = [&]() { xd.release(); td.release(); pd.release(); sd.release(); me.release(); Md.release(); ed.release(); cd.release(); };
+    auto cleanup = [&]() { cudaStreamSynchronize(h->st); xd.release(false); td.release(false); pd.release(false); sd.release(false); me.release(false); Md.release(false); ed.release(false); cd.release(false); };
     cudaError_t e = upload(xd, x, (size_t)nx, h->st);
     if (e == cudaSuccess) e = upload(td, tau, (size_t)n, h->st);
     if (e == cudaSuccess) e = upload(pd, pts, (size_t)3 * n, h->st);

@@ -195,7 +195,7 @@ extern "C" int mvus_ba_spl_create(int32_t device, int64_t m, int32_t idim, int32
     mvus_spl_ctx* h = new mvus_spl_ctx();
     h->device = device; h->m = m; h->idim = idim; h->k = k;
     cudaError_t e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&h->h_pin, 8 * sizeof(double));
+    if (e == cudaSuccess) { h->h_pin = mvus::pin_scratch_acquire(); if (!h->h_pin) e = cudaErrorMemoryAllocation; }
     if (e == cudaSuccess) e = mvus::upload(h->u, u, (size_t)m, h->st);
     if (e == cudaSuccess) e = mvus::upload(h->x, x, (size_t)m * idim, h->st);
     if (e == cudaSuccess) e = h->term.alloc((size_t)m);
@@ -209,9 +209,10 @@ extern "C" int mvus_ba_spl_create(int32_t device, int64_t m, int32_t idim, int32
 extern "C" void mvus_ba_spl_destroy(mvus_spl_handle h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaDeviceSynchronize();
+    if (h->st) cudaStreamSynchronize(h->st);
+    cudaStreamSynchronize(cudaStreamPerThread);
     for (auto* b : {&h->u, &h->x, &h->t, &h->G, &h->rhs, &h->c, &h->fpint, &h->term, &h->scal, &h->pen}) b->release(false);
-    if (h->h_pin) cudaFreeHost(h->h_pin);
+    mvus::pin_scratch_release(h->h_pin);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
 }
