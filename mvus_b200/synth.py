@@ -137,6 +137,8 @@ def make_flight(nc=4, det_per_cam=1500, frames_per_knot=15.0, seed=0, noise=0.5,
     beta = np.zeros(nc)
     beta[1:] = rng_f.uniform(-40.0, 40.0, nc - 1)
     rho = rng_f.uniform(0.1, 0.8, nc) if rolling_shutter else np.zeros(nc)
+    if rho_true is not None:                      # (tests: read-out speeds outside [0, 1] make the rs bounds active)
+        rho = np.asarray(rho_true, dtype=np.float64).copy()
 
     flight = Scene()
     flight.numCam = nc
@@ -227,8 +229,6 @@ def write_dataset(out_dir, nc=4, det_per_cam=5000, seed=0, noise=0.5, rolling_sh
     cf[1:] = np.round(rng_f.uniform(-60, 60, nc - 1))
     beta = cf[0] - alpha * cf
     rho = rng_f.uniform(0.1, 0.8, nc) if rolling_shutter else np.zeros(nc)
-    if rho_true is not None:                      # (tests: read-out speeds outside [0, 1] make the rs bounds active)
-        rho = np.asarray(rho_true, dtype=np.float64).copy()
     det_paths, cam_paths = [], []
     for i, cam in enumerate(cams):
         f0 = int(np.ceil((0.0 - beta[i]) / alpha[i]))
