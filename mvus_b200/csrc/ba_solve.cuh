@@ -509,21 +509,31 @@ chol_panel_kernel(double* __restrict__ S, int lds, int n, int p0, int* __restric
         L[r][c] = (r < nb && c <= r) ? S[(int64_t)(p0 + r) * lds + p0 + c] : (r == c ? 1.0 : 0.0);
     }
     __syncthreads();
-    for (int j = 0; j < nb; ++j) {
-        double d = L[j][j];
-        const bool bad = !(d > 0.0);
-        d = sqrt(bad ? 1.0 : d);
-        if (bad && tid == 0 && blockIdx.x == 0) atomicExch(fail_flag, 1);
-        __syncthreads();
-        if (tid == 0) L[j][j] = d;
-        if (tid > j && tid < nb) L[tid][j] /= d;
-        __syncthreads();
-        for (int e = tid; e < CH_B * CH_B; e += 256) {
-            const int r = e / CH_B, c = e - r * CH_B;
-            if (c > j && c <= r && r < nb) L[r][c] -= L[r][j] * L[c][j];
+    // 32 x 32 Cholesky on ONE warp, rows in registers (lane = row): pivot and multipliers travel by shuffles, no
+    // barrier inside the 32 dependent steps (the 256-thread version with three __syncthreads per step took ~15 us)
+    if (tid < 32) {
+        double row[CH_B];
+#pragma unroll
+        for (int c = 0; c < CH_B; ++c) row[c] = L[tid][c];
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < CH_B; ++j) {
+            double d = __shfl_sync(0xffffffffu, row[j], j);
+            if (!(d > 0.0)) { bad = bad || j < nb; d = 1.0; }
+            const double inv = 1.0 / sqrt(d);
+            const double lij = row[j] * inv;               // lane i >= j: L[i][j]
+            row[j] = lij;
+#pragma unroll
+            for (int k2 = j + 1; k2 < CH_B; ++k2) {
+                const double lkj = __shfl_sync(0xffffffffu, lij, k2);
+                row[k2] -= lij * lkj;                      // entry (i, k2), meaningful for k2 <= i
+            }
         }
-        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < CH_B; ++c) L[tid][c] = row[c];
+        if (bad && tid == 0 && blockIdx.x == 0) atomicExch(fail_flag, 1);
     }
+    __syncthreads();
     if (blockIdx.x == 0)
         for (int i = tid; i < CH_B * CH_B; i += 256) {
             const int r = i / CH_B, c = i - r * CH_B;
