@@ -296,11 +296,24 @@ chunk_w_kernel(int64_t nb, int Lc, int64_t c_first, int ldw, const double* __res
             const double* Zh = sm[st] + QQ;
             const double* Zr = sm[st] + 2 * QQ;
             const double* Li = sm[st] + 3 * QQ;
+            // (the matrices are read as shared-memory broadcasts: one LDS per FMA made the kernel L1TEX-bound at
+            //  87 % -- for even Q two neighbouring entries come with one 16-byte load)
+            constexpr bool V2 = (Q % 2 == 0);
 #pragma unroll
             for (int i = 0; i < Q; ++i) {
                 double v = w[i];
+                if (V2) {
 #pragma unroll
-                for (int kk = 0; kk < i; ++kk) v -= Lm[i * Q + kk] * w[kk];
+                    for (int kk = 0; kk + 1 < i; kk += 2) {
+                        const double2 l2 = *reinterpret_cast<const double2*>(Lm + i * Q + kk);
+                        v -= l2.x * w[kk];
+                        v -= l2.y * w[kk + 1];
+                    }
+                    if (i & 1) v -= Lm[i * Q + i - 1] * w[i - 1];
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < i; ++kk) v -= Lm[i * Q + kk] * w[kk];
+                }
                 w[i] = v * Li[i];
             }
             if (act) {
@@ -310,15 +323,18 @@ chunk_w_kernel(int64_t nb, int Lc, int64_t c_first, int ldw, const double* __res
 #pragma unroll
             for (int b = 0; b < Q; ++b) {
                 const double x = w[b];
+                if (V2) {
 #pragma unroll
-                for (int a = 0; a < Q; ++a) wh[a] -= Zh[b * Q + a] * x;
-            }
-            // -ZR_k^T W~_k goes to the next block's rows (or, after the last block, to the next head)
+                    for (int a = 0; a < Q; a += 2) {
+                        const double2 h2 = *reinterpret_cast<const double2*>(Zh + b * Q + a);
+                        const double2 r2 = *reinterpret_cast<const double2*>(Zr + b * Q + a);
+                        wh[a] -= h2.x * x; wh[a + 1] -= h2.y * x;
+                        wnx[a] -= r2.x * x; wnx[a + 1] -= r2.y * x;     // -ZR_k^T W~_k: next block's rows / next head
+                    }
+                } else {
 #pragma unroll
-            for (int b = 0; b < Q; ++b) {
-                const double x = w[b];
-#pragma unroll
-                for (int a = 0; a < Q; ++a) wnx[a] -= Zr[b * Q + a] * x;
+                    for (int a = 0; a < Q; ++a) { wh[a] -= Zh[b * Q + a] * x; wnx[a] -= Zr[b * Q + a] * x; }
+                }
             }
         }
     }
