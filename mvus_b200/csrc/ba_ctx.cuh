@@ -135,6 +135,10 @@ struct mvus_ba_ctx {
     size_t w_guard = 0;                  // doubles in front of W~ inside the allocation W (K2's guard rows)
     double* Wp() const { return W.p ? W.p + w_guard : nullptr; }
     int launches = 0;
+    // CUDA graph of the linear solve's launch sequence (small single-GPU systems, ba_solve.cuh: solve_damped):
+    // 0 = not tried, 1 = ran once directly, 2 = captured, -1 = capture failed / not used
+    int graph_state = 0, graph_launches = 0;
+    cudaGraphExec_t solve_graph = nullptr;
     bool verbose = false;                // MVUS_BA_VERBOSE, read once at mvus_ba_create
     double band_lo = 0.5, band_hi = 1.5; // trust-region band (MVUS_BA_BAND_LO / _HI at create: experiments only)
     int64_t cost_slot = 0;        // index in `partial` where the last evaluation left sum r^2

@@ -91,14 +91,14 @@ __global__ void diag_kernel(const double* __restrict__ A, const double* __restri
     }
 }
 
-__global__ void damp_copy_kernel(const double* __restrict__ D, const double* __restrict__ diag_s, double lam,
+__global__ void damp_copy_kernel(const double* __restrict__ D, const double* __restrict__ diag_s, const double* __restrict__ lam_p,
                                  int64_t nbq, int q, int64_t n_ctrl3, double* __restrict__ Dw) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over nb*q*q
     if (i >= nbq * q) return;
     const int64_t row = i / q;
     const int col = (int)(i - row * q), l = (int)(row % q);
     double v = l <= col ? D[i] : D[(row - l + col) * q + l];      // D holds its upper triangle (K2, K2m)
-    if (l == col) v = row < n_ctrl3 ? v + lam * diag_s[row] : 1.0;
+    if (l == col) v = row < n_ctrl3 ? v + lam_p[0] * diag_s[row] : 1.0;
     Dw[i] = v;
 }
 
@@ -469,7 +469,7 @@ __global__ void freeze_cols_kernel(double* __restrict__ Ww, int64_t rows, int ld
 
 // S = blockdiag(A) [+ Ax] + lam * diag - S~ (lower triangle), rhs = bc - S~[ncP][:]
 __global__ void form_schur_kernel(const double* __restrict__ A, const double* __restrict__ bc,
-                                  const double* __restrict__ diag_c, double lam, int nc, int Pc, int ldw,
+                                  const double* __restrict__ diag_c, const double* __restrict__ lam_p, int nc, int Pc, int ldw,
                                   const int* __restrict__ frozen, const double* __restrict__ Ax,
                                   double* __restrict__ Sfull, double* __restrict__ rhs) {
     const int ncP = nc * Pc;
@@ -482,7 +482,7 @@ __global__ void form_schur_kernel(const double* __restrict__ A, const double* __
     if (cr == cc) v += A[((int64_t)cr * Pc + (row - cr * Pc)) * Pc + (col - cc * Pc)];
     else if (Ax) v += Ax[(int64_t)row * ncP + col];          // cross-camera entries (points mode, ba_points.cuh)
     if (row == col) {
-        v += lam * diag_c[row];
+        v += lam_p[0] * diag_c[row];
         rhs[row] = frozen[row] ? 0.0 : bc[row] - Sfull[(int64_t)ncP * ldw + row];
     }
     if (frozen[row] || frozen[col]) v = (row == col) ? 1.0 : 0.0;
@@ -1141,48 +1141,97 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
     double* sW = pre ? h->Wh.p : h->Ww.p;
     double* sZ = pre ? h->ZLh.p : h->ZL.p;
     double* sd = pre ? h->dsh.p : h->dlt_s.p;
-    MV_CUDA(h, cudaMemsetAsync(fail_flag, 0, sizeof(int), h->st));
-    MV_CUDA(h, cudaMemsetAsync(h->Sd.p, 0, h->Sd.bytes(), h->st));
+    // lambda travels through device memory (xs[12]) so that the launch sequence below does not depend on it
+    const double* lam_p = h->xs.p + 12;
+    h->h_pin[16] = lam;
+    MV_CUDA(h, cudaMemcpyAsync(h->xs.p + 12, h->h_pin + 16, sizeof(double), cudaMemcpyHostToDevice, h->st));
     if (h->world <= 1) {
         // ---------------- single GPU: (chunk pre-reduction +) full cyclic reduction + root ----------------
-        damp_copy_kernel<<<(int)((nbq * q + 255) / 256), 256, 0, h->st>>>(h->D.p, h->diag_s.p, lam, nbq, q,
-                                                                          3 * h->n_ctrl, h->Dw.p);
-        MV_CUDA(h, cudaMemcpyAsync(h->Ew.p, h->E.p, nb * qq * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-        h->launches += 1;
-        const double* wsrc = h->Wp();          // first touch of every block reads W~ directly: no 2|W~| copy pass
-        if (h->desc.rs_bounds) {               // frozen columns must be zeroed in a private copy
-            MV_CUDA(h, cudaMemcpyAsync(h->Ww.p, h->Wp(), (size_t)nbq * ldw * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
-            freeze_cols_kernel<<<(int)((nbq + 255) / 256), 256, 0, h->st>>>(h->Ww.p, nbq, ldw, h->nc, h->Pc, h->frozen.p);
+        // The launch sequence is the same for every solve of a handle.  For SMALL systems, where the ~25-60
+        // launches cost more than the kernels (config 5: 370 launches per problem, throughput bound by the launch
+        // rate; config 2), it is captured into a CUDA graph at the handle's second solve and replayed afterwards.
+        auto single_body = [&](bool timing) -> int {
+            MV_CUDA(h, cudaMemsetAsync(fail_flag, 0, sizeof(int), h->st));
+            MV_CUDA(h, cudaMemsetAsync(h->Sd.p, 0, h->Sd.bytes(), h->st));
+            damp_copy_kernel<<<(int)((nbq * q + 255) / 256), 256, 0, h->st>>>(h->D.p, h->diag_s.p, lam_p, nbq, q,
+                                                                              3 * h->n_ctrl, h->Dw.p);
+            MV_CUDA(h, cudaMemcpyAsync(h->Ew.p, h->E.p, nb * qq * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+            h->launches += 1;
+            const double* wsrc = h->Wp();          // first touch of every block reads W~ directly: no 2|W~| copy pass
+            if (h->desc.rs_bounds) {               // frozen columns must be zeroed in a private copy
+                MV_CUDA(h, cudaMemcpyAsync(h->Ww.p, h->Wp(), (size_t)nbq * ldw * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
+                freeze_cols_kernel<<<(int)((nbq + 255) / 256), 256, 0, h->st>>>(h->Ww.p, nbq, ldw, h->nc, h->Pc, h->frozen.p);
+                h->launches++;
+                wsrc = h->Ww.p;
+            }
+            if (timing) cudaEventRecord(h->evs[0], h->st);
+            BcrView v{sD, sE, sW, sZ, sd, pre ? h->nh : nb};
+            if (pre) prereduce_range(h, 0, nb, wsrc, fail_flag);
+            else if (!h->desc.rs_bounds) v.Worig = wsrc;
+            std::vector<int64_t> levels = bcr_eliminate(h, v, v.nb, true, fail_flag);
+            if (pre) {                             // the heads' rows join the eliminated ones for the SYRK
+                head_rows_kernel<<<(int)h->nh, 256, 0, h->st>>>(0, Lc, q, ldw, h->Wh.p, h->Ww.p);
+                h->launches++;
+            }
+            if (timing) cudaEventRecord(h->evs[1], h->st);
+            launch_syrk(h, h->Ww.p, nbq, h->Sd.p);
+            if (timing) { cudaEventRecord(h->evs[2], h->st); timed = true; }
+            form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
+                h->A.p, bc, h->diag_c.p, lam_p, h->nc, h->Pc, ldw, h->frozen.p, h->Ax.p, h->Sd.p, rhs);
             h->launches++;
-            wsrc = h->Ww.p;
-        }
-        cudaEventRecord(h->evs[0], h->st);
-        BcrView v{sD, sE, sW, sZ, sd, pre ? h->nh : nb};
-        if (pre) prereduce_range(h, 0, nb, wsrc, fail_flag);
-        else if (!h->desc.rs_bounds) v.Worig = wsrc;
-        std::vector<int64_t> levels = bcr_eliminate(h, v, v.nb, true, fail_flag);
-        if (pre) {                             // the heads' rows join the eliminated ones for the SYRK
-            head_rows_kernel<<<(int)h->nh, 256, 0, h->st>>>(0, Lc, q, ldw, h->Wh.p, h->Ww.p);
+            dense_chol_solve(h, h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
+            wdc_kernel<<<(int)((nbq * 32 + 255) / 256), 256, 0, h->st>>>(h->Ww.p, h->dlt_c.p, nbq, ldw, h->dlt_s.p);
             h->launches++;
+            if (pre) {
+                wdc_kernel<<<(int)((h->nh * q * 32 + 255) / 256), 256, 0, h->st>>>(h->Wh.p, h->dlt_c.p, h->nh * q, ldw, h->dsh.p);
+                h->launches++;
+            }
+            bcr_back(h, v, levels, true);
+            if (pre) chunk_back_range(h, 0, nb);
+            MV_CUDA(h, cudaGetLastError());
+            return MVUS_OK;
+        };
+        const bool small = (int64_t)nbq * ldw <= ((int64_t)8 << 20);          // W~ up to 64 MB
+        if (!small || h->graph_state < 0) {
+            const int rc = single_body(true);
+            if (rc) return rc;
+        } else if (h->graph_state == 0) {                 // first solve: direct (function attributes, allocations)
+            const int rc = single_body(false);
+            if (rc) return rc;
+            h->graph_state = 1;
+        } else {
+            if (h->graph_state == 1) {
+                cudaGraph_t g = nullptr;
+                cudaError_t ce = cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal);
+                int rc = MVUS_OK;
+                if (ce == cudaSuccess) {
+                    const int l0 = h->launches;
+                    rc = single_body(false);
+                    h->graph_launches = h->launches - l0;
+                    ce = cudaStreamEndCapture(h->st, &g);
+                }
+                if (rc == MVUS_OK && ce == cudaSuccess && g) ce = cudaGraphInstantiate(&h->solve_graph, g, 0);
+                if (g) cudaGraphDestroy(g);
+                if (rc != MVUS_OK || ce != cudaSuccess || !h->solve_graph) {
+                    cudaGetLastError();
+                    h->solve_graph = nullptr;
+                    h->graph_state = -1;                  // capture not possible here: direct launches from now on
+                    const int rc2 = single_body(true);
+                    if (rc2) return rc2;
+                } else {
+                    h->graph_state = 2;
+                    h->launches -= h->graph_launches;     // (counted again by the replay below)
+                }
+            }
+            if (h->graph_state == 2) {
+                MV_CUDA(h, cudaGraphLaunch(h->solve_graph, h->st));
+                h->launches += h->graph_launches;
+            }
         }
-        cudaEventRecord(h->evs[1], h->st);
-        launch_syrk(h, h->Ww.p, nbq, h->Sd.p);
-        cudaEventRecord(h->evs[2], h->st);
-        timed = true;
-        form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
-            h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->frozen.p, h->Ax.p, h->Sd.p, rhs);
-        h->launches++;
-        dense_chol_solve(h, h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
-        wdc_kernel<<<(int)((nbq * 32 + 255) / 256), 256, 0, h->st>>>(h->Ww.p, h->dlt_c.p, nbq, ldw, h->dlt_s.p);
-        h->launches++;
-        if (pre) {
-            wdc_kernel<<<(int)((h->nh * q * 32 + 255) / 256), 256, 0, h->st>>>(h->Wh.p, h->dlt_c.p, h->nh * q, ldw, h->dsh.p);
-            h->launches++;
-        }
-        bcr_back(h, v, levels, true);
-        if (pre) chunk_back_range(h, 0, nb);
     } else {
         // ---------------- sharded solve ----------------
+        MV_CUDA(h, cudaMemsetAsync(fail_flag, 0, sizeof(int), h->st));
+        MV_CUDA(h, cudaMemsetAsync(h->Sd.p, 0, h->Sd.bytes(), h->st));
         // Super-blocks are cut into chunks of Bc (power of two); this rank owns chunks [c0, c1).  With the
         // pre-reduction (Lc > 1, Lc divides Bc) the own range is first reduced to its chunk heads; "blocks"
         // below are then heads and Bc counts heads.
@@ -1197,7 +1246,7 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
         const double* wsrc = h->Wp();
         if (nloc > 0) {
             damp_copy_kernel<<<(int)((nloc * q * q + 255) / 256), 256, 0, h->st>>>(
-                h->D.p + lo * qq, h->diag_s.p + lo * q, lam, nloc * q, q,
+                h->D.p + lo * qq, h->diag_s.p + lo * q, lam_p, nloc * q, q,
                 std::max<int64_t>(0, 3 * h->n_ctrl - lo * q), h->Dw.p + lo * qq);
             MV_CUDA(h, cudaMemcpyAsync(h->Ew.p + lo * qq, h->E.p + lo * qq, nloc * qq * sizeof(double), cudaMemcpyDeviceToDevice, h->st));
             h->launches++;
@@ -1256,7 +1305,7 @@ inline int solve_damped(mvus_ba_ctx* h, double lam, int* ok) {
         e = nccl_sum(h, h->Sd.p, (size_t)ldw * ldw);
         if (e) return e;
         form_schur_kernel<<<(int)(((int64_t)h->ncP * h->ncP + 255) / 256), 256, 0, h->st>>>(
-            h->A.p, bc, h->diag_c.p, lam, h->nc, h->Pc, ldw, h->frozen.p, h->Ax.p, h->Sd.p, rhs);
+            h->A.p, bc, h->diag_c.p, lam_p, h->nc, h->Pc, ldw, h->frozen.p, h->Ax.p, h->Sd.p, rhs);
         h->launches++;
         dense_chol_solve(h, h->Sd.p, ldw, h->ncP, rhs, h->dlt_c.p, fail_flag);
         e = nccl_bcast0(h, h->dlt_c.p, (size_t)h->ncP);

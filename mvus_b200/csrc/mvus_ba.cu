@@ -151,6 +151,7 @@ extern "C" void mvus_ba_destroy(mvus_ba_handle h) {
         b->release(false);
     h->tau_flag.release(false);
     h->sort_tmp.release(false);
+    if (h->solve_graph) cudaGraphExecDestroy(h->solve_graph);
     pin_scratch_release(h->h_pin);
     for (int k = 0; k < 8; ++k) if (h->ev[k]) cudaEventDestroy(h->ev[k]);
     for (int k = 0; k < 6; ++k) if (h->evs[k]) cudaEventDestroy(h->evs[k]);
@@ -238,6 +239,8 @@ static cudaError_t upload_segments(int device, const std::vector<UploadSeg>& seg
 // world size at the first solve.  Any later mvus_ba_set_detections / set_splines / comm_init must
 // make solver_alloc run again, or K2 and the cyclic-reduction levels would use stale block counts.
 void mvus::invalidate_solver(mvus_ba_ctx* h) {
+    if (h->solve_graph) { cudaGraphExecDestroy(h->solve_graph); h->solve_graph = nullptr; }
+    if (h->graph_state > 0) h->graph_state = 0;
     if (h->st) cudaStreamSynchronize(h->st);      // (the handle's own stream is the only user of these)
     h->A.release(false);
     h->W.release(false);
