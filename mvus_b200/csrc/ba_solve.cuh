@@ -179,24 +179,28 @@ bcr_level_kernel(int64_t nb, int ldw, int64_t s, int64_t sp, int root, int odd_o
     }
     __syncthreads();
     if (elim) {
-        // Cholesky of Dj (lower, in place), q <= 18: one warp, column by column
+        // Cholesky of Dj (lower, in place), q <= 18: one warp, rows in registers (lane = row), pivot and
+        // multipliers by shuffles -- no shared-memory round trips inside the q dependent steps
         if (tid < 32) {
-#pragma unroll 1
-            for (int c = 0; c < q; ++c) {
-                double d = Dj[c * q + c];
-                if (!(d > 0.0)) { if (tid == 0) s_bad = 1; d = 1.0; }
-                d = sqrt(d);
-                __syncwarp();
-                if (tid == 0) Dj[c * q + c] = d;
-#pragma unroll 1
-                for (int i = c + 1 + tid; i < q; i += 32) Dj[i * q + c] /= d;
-                __syncwarp();
-#pragma unroll 1
-                for (int i = c + 1 + tid; i < q; i += 32)
-#pragma unroll 1
-                    for (int k = c + 1; k <= i; ++k) Dj[i * q + k] -= Dj[i * q + c] * Dj[k * q + c];
-                __syncwarp();
+            double row[Q];
+#pragma unroll
+            for (int c = 0; c < Q; ++c) row[c] = tid < Q ? Dj[tid * Q + c] : 0.0;
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < Q; ++c) {
+                double d = __shfl_sync(0xffffffffu, row[c], c);
+                if (!(d > 0.0)) { bad = true; d = 1.0; }
+                const double inv = 1.0 / sqrt(d);
+                const double lic = row[c] * inv;
+                row[c] = lic;
+#pragma unroll
+                for (int k2 = c + 1; k2 < Q; ++k2) row[k2] -= lic * __shfl_sync(0xffffffffu, lic, k2);
             }
+            if (tid < Q) {
+#pragma unroll
+                for (int c = 0; c < Q; ++c) Dj[tid * Q + c] = row[c];
+            }
+            if (bad && tid == 0) s_bad = 1;
         }
         __syncthreads();
         // ZL = L^-1 El, ZR = L^-1 Er : thread per column of [El | Er]
@@ -659,35 +663,37 @@ __global__ void wdc_kernel(const double* __restrict__ Ww, const double* __restri
 __global__ void bcr_back_kernel(int64_t nb, int q, int64_t s, int root, const double* __restrict__ Dw,
                                 const double* __restrict__ Ew, const double* __restrict__ ZL,
                                 double* __restrict__ ds) {
-    __shared__ double v[QMAX];
     const int64_t k = root ? 0 : ((int64_t)blockIdx.x * 2 + 1) * s;
     if (k >= nb) return;
-    const int qq = q * q, a = threadIdx.x;
-    if (a < q) {
-        double acc = ds[k * q + a];
-        if (!root) {
-            const double* zl = ZL + k * qq + a * q;
-            const double* dl = ds + (k - s) * q;
-            for (int b = 0; b < q; ++b) acc -= zl[b] * dl[b];
-            if (k + s < nb) {
-                const double* zr = Ew + k * qq + a * q;
-                const double* dr = ds + (k + s) * q;
-                for (int b = 0; b < q; ++b) acc -= zr[b] * dr[b];
-            }
-        }
-        v[a] = acc;
-    }
-    __syncwarp();
-    if (a == 0) {
-        const double* L = Dw + k * qq;
-        for (int i = q - 1; i >= 0; --i) {
-            double t = v[i];
-            for (int c = i + 1; c < q; ++c) t -= L[c * q + i] * v[c];
-            v[i] = t / L[i * q + i];
+    const int qq = q * q, lane = threadIdx.x;
+    const int a = lane < q ? lane : 0;
+    double v = ds[k * q + a];
+    if (!root) {
+        const double* zl = ZL + k * qq + a * q;
+        const double* dl = ds + (k - s) * q;
+        for (int b = 0; b < q; ++b) v -= zl[b] * dl[b];
+        if (k + s < nb) {
+            const double* zr = Ew + k * qq + a * q;
+            const double* dr = ds + (k + s) * q;
+            for (int b = 0; b < q; ++b) v -= zr[b] * dr[b];
         }
     }
-    __syncwarp();
-    if (a < q) ds[k * q + a] = v[a];
+    // x = L^-T v on one warp: lane a keeps column a of L (L[i][a], i >= a); x_i leaves lane i by shuffle and the
+    // lanes below it update their v (the version with one thread walking the triangle took ~13 us per level)
+    const double* L = Dw + k * qq;
+    double lcol[QMAX];
+#pragma unroll
+    for (int i = 0; i < QMAX; ++i) lcol[i] = i < q ? L[i * q + a] : 0.0;
+    double x = 0.0;
+#pragma unroll
+    for (int i = QMAX - 1; i >= 0; --i) {
+        if (i < q) {
+            const double xi = __shfl_sync(0xffffffffu, v, i) / __shfl_sync(0xffffffffu, lcol[i], i);
+            if (a == i) x = xi;
+            if (a < i) v -= lcol[i] * xi;
+        }
+    }
+    if (lane < q) ds[k * q + lane] = x;
 }
 
 // ------------------------------------------------------------------------------------------
