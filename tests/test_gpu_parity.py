@@ -127,12 +127,17 @@ def test_cost_not_above_shipped(name, built_lib):
     hd.close()
 
 
-@pytest.mark.parametrize('name', ['gs_plain', 'rs_F_gap', 'calib_KE', 'rs_bounds_dense'])
+@pytest.mark.parametrize('name', ['gs_plain', 'rs_F_gap', 'calib_KE', 'rs_bounds_dense', 'rs_F_gap:4.0', 'rs_F_gap:5.0'])
 def test_chunk_prereduction_is_the_same_solve(name, built_lib):
     """The chunk pre-reduction in front of the cyclic reduction (csrc/ba_chunk.cuh, desc.solver_chunk) is
     an exact reordering of the same elimination: a 4-evaluation and a 10-evaluation solve must agree with the
     cyclic-reduction-only solve (chunk lengths that divide the block count and ragged ones)."""
-    fl, fp, prob, _ = _setup(name)
+    if ':' in name:          # denser knots: motion rows span more control points -> wider super-blocks (q = 15, 18)
+        base, fpk = name.split(':')
+        fl, truth, bakw = cases.make(base, frames_per_knot=float(fpk))
+        fp = FlatProblem(fl, fl.numCam, **bakw)
+    else:
+        fl, fp, prob, _ = _setup(name)
     base1 = base10 = None
     for chunk in (1, 2, 5, 64):
         h1 = _cabi.Handle(fp, max_nfev=4, solver_chunk=chunk)

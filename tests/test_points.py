@@ -145,3 +145,16 @@ def test_motion_prior_mode_through_the_dropin(built_lib):
     assert abs(res.cost - res_ref.cost) <= 1e-9 * res.cost and res.nfev == res_ref.nfev
     assert np.abs(res.x - res_ref.x).max() <= 1e-9 * np.abs(res.x).max()
     assert np.allclose(np.asarray(ref.spline['int']), np.asarray(fl.spline['int']), rtol=1e-9, atol=1e-9)
+
+
+def test_reference_placement_matches_oracle():
+    """mvus_b200.points.reference_placement (host logic of res.fun's row order) against the oracle's restatement of
+    the reference's np.intersect1d scatter, on time stamps with crossings."""
+    from mvus_b200 import points
+    fl, kw, gold, pp = _case('points_F')
+    x = gold['xs'][2]                                   # perturbed alpha / beta: some time stamps have crossed
+    ts = pp.timestamps(x)
+    assert (np.diff(ts) <= 0).any()
+    gid, prev, nxt = pp.neighbours(ts)
+    rows = np.nonzero((gid > 0) & (prev >= 0) & (nxt >= 0))[0]
+    assert np.array_equal(points.reference_placement(ts, rows, gid), pp.placement(ts, rows, gid))
