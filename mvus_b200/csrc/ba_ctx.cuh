@@ -114,6 +114,7 @@ struct mvus_ba_ctx {
     mvus::DevBuf<int> span, mbase, flag, frozen;
     // K2 work list: chunks of up to 4 consecutive tiles of one camera, visited in time order
     int n_chunks = 0;
+    bool chunk_sorted = false;          // chunk_perm is valid for the current inputs / start point (accumulate)
     mvus::DevBuf<int> chunk_tile0, chunk_nt, chunk_key, chunk_key2, chunk_id, chunk_perm, k2_queue;
     mvus::DevBuf<unsigned char> sort_tmp;
     double* h_pin = nullptr;      // pinned scratch for scalars

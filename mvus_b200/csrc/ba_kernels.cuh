@@ -121,6 +121,64 @@ resjac_kernel(SplineView sp, const double* __restrict__ x, const double* __restr
     if (threadIdx.x == 0) partial[tl] = s;
 }
 
+// K1, residual only (trial evaluations of the LM loop): TWO tiles per CTA, each thread carries one detection of
+// each tile.  The per-detection work is one dependent chain of loads (frame -> time -> bucket -> span ->
+// polynomial row -> coefficients); at 40 B of HBM traffic per detection the one-detection-per-thread kernel ran
+// at 0.21 of the HBM roofline on that latency.  Two independent chains per thread double the loads in flight.
+// grid = ceil(n_tiles / 2), block = TILE_DET.  partial[] keeps one slot per tile (the second one is zeroed).
+template <bool CALIB>
+__global__ void __launch_bounds__(TILE_DET)
+residual2_kernel(SplineView sp, const double* __restrict__ x, const double* __restrict__ camprep,
+                 const int* __restrict__ tile_cam, const int64_t* __restrict__ tile_start,
+                 const int* __restrict__ tile_cnt, const int64_t* __restrict__ row_off,
+                 const double* __restrict__ frame, const double* __restrict__ xr,
+                 const double* __restrict__ yr, const double* __restrict__ obs_u,
+                 const double* __restrict__ obs_v, int undist, int opt_sync, int opt_rs, int n_tiles,
+                 double* __restrict__ r, double* __restrict__ partial) {
+    __shared__ double s_cam[2][CAMPREP_DOUBLES];
+    __shared__ double s_red[TILE_DET / 32];
+    const int ta = 2 * blockIdx.x, tb = ta + 1;
+    const bool hasb = tb < n_tiles;
+    const int cama = tile_cam[ta], camb = hasb ? tile_cam[tb] : cama;
+    for (int k = threadIdx.x; k < CAMPREP_DOUBLES; k += blockDim.x) {
+        s_cam[0][k] = camprep[(size_t)cama * CAMPREP_DOUBLES + k];
+        s_cam[1][k] = camprep[(size_t)camb * CAMPREP_DOUBLES + k];
+    }
+    __syncthreads();
+    const CamPrep& ca = *reinterpret_cast<const CamPrep*>(s_cam[0]);
+    const CamPrep& cb = *reinterpret_cast<const CamPrep*>(s_cam[1]);
+    const bool ina = (int)threadIdx.x < tile_cnt[ta], inb = hasb && (int)threadIdx.x < tile_cnt[tb];
+    const int64_t da = tile_start[ta] + threadIdx.x, db = hasb ? tile_start[tb] + threadIdx.x : da;
+    // all inputs of both detections first
+    double fa = 0.0, ya = 0.0, xa = 0.0, oua = 0.0, ova = 0.0, fb = 0.0, yb = 0.0, xb = 0.0, oub = 0.0, ovb = 0.0;
+    if (ina) {
+        fa = __ldcs(frame + da); ya = __ldcs(yr + da);
+        if (CALIB) xa = __ldcs(xr + da); else { oua = __ldcs(obs_u + da); ova = __ldcs(obs_v + da); }
+    }
+    if (inb) {
+        fb = __ldcs(frame + db); yb = __ldcs(yr + db);
+        if (CALIB) xb = __ldcs(xr + db); else { oub = __ldcs(obs_u + db); ovb = __ldcs(obs_v + db); }
+    }
+    FreeMask fm{opt_sync != 0, opt_rs != 0};
+    NullSink sink;
+    double rua = 0.0, rva = 0.0, rub = 0.0, rvb = 0.0;
+    int spa, spb;
+    if (ina) resjac_one<CALIB, false>(ca, undist != 0, fm, fa, xa, ya, oua, ova, sp, x, rua, rva, spa, sink);
+    if (inb) resjac_one<CALIB, false>(cb, undist != 0, fm, fb, xb, yb, oub, ovb, sp, x, rub, rvb, spb, sink);
+    if (ina) {
+        const int64_t r0 = row_off[cama], ncam = (row_off[cama + 1] - r0) >> 1, local = da - (r0 >> 1);
+        __stcs(r + r0 + local, rua);
+        __stcs(r + r0 + ncam + local, rva);
+    }
+    if (inb) {
+        const int64_t r0 = row_off[camb], ncam = (row_off[camb + 1] - r0) >> 1, local = db - (r0 >> 1);
+        __stcs(r + r0 + local, rub);
+        __stcs(r + r0 + ncam + local, rvb);
+    }
+    const double s = block_sum_128(rua * rua + rva * rva + rub * rub + rvb * rvb, s_red);
+    if (threadIdx.x == 0) { partial[ta] = s; if (hasb) partial[tb] = 0.0; }
+}
+
 // K1m.  grid = ceil(M / 128), block = 128.
 template <bool WANTJ>
 __global__ void __launch_bounds__(128)

@@ -892,20 +892,26 @@ inline int accumulate(mvus_ba_ctx* h) {
         MV_CUDA(h, h->chunk_id.alloc(nch));
         MV_CUDA(h, h->chunk_perm.alloc(nch));
         MV_CUDA(h, h->k2_queue.alloc(4));
-        size_t tb = 0;
-        MV_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, h->chunk_key.p, h->chunk_key2.p, h->chunk_id.p,
-                                                   h->chunk_perm.p, nch, 0, 32, h->st));
-        MV_CUDA(h, h->sort_tmp.alloc(tb));
-        const int blk_d = jblk_doubles(h->P);
-        chunk_key_kernel<<<(nch + 255) / 256, 256, 0, h->st>>>(h->J.p, blk_d, blk_d - 16, h->chunk_tile0.p, nch,
-                                                              h->chunk_key.p, h->chunk_id.p);
-        MV_CUDA(h, cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tb, h->chunk_key.p, h->chunk_key2.p, h->chunk_id.p,
-                                                   h->chunk_perm.p, nch, 0, 32, h->st));
+        // (the order only serves L2 locality of the RED targets, and the spans move little between the evaluations
+        //  of one solve: sorted at the first accumulation after the inputs / the start point changed, reused afterwards)
+        if (!h->chunk_sorted) {
+            size_t tb = 0;
+            MV_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, tb, h->chunk_key.p, h->chunk_key2.p, h->chunk_id.p,
+                                                       h->chunk_perm.p, nch, 0, 32, h->st));
+            MV_CUDA(h, h->sort_tmp.alloc(tb));
+            const int blk_d = jblk_doubles(h->P);
+            chunk_key_kernel<<<(nch + 255) / 256, 256, 0, h->st>>>(h->J.p, blk_d, blk_d - 16, h->chunk_tile0.p, nch,
+                                                                  h->chunk_key.p, h->chunk_id.p);
+            MV_CUDA(h, cub::DeviceRadixSort::SortPairs(h->sort_tmp.p, tb, h->chunk_key.p, h->chunk_key2.p, h->chunk_id.p,
+                                                       h->chunk_perm.p, nch, 0, 32, h->st));
+            h->chunk_sorted = true;
+            h->launches += 2;
+        }
         {   // [0] work queue, [1] smallest, [2] largest block-of-four-spans any warp saw (the touched rows)
             const int init[3] = {0, 0x7fffffff, -1};
             MV_CUDA(h, cudaMemcpyAsync(h->k2_queue.p, init, sizeof(init), cudaMemcpyHostToDevice, h->st));
         }
-        h->launches += 3;
+        h->launches += 1;
         const int64_t n_rows = (int64_t)(h->nb + 1) * h->q;
         if ((n_rows + 2 * K2_GUARD) * (int64_t)h->ldw >= ((int64_t)1 << 32))        // K2 flushes with 32-bit offsets
             return fail(h, MVUS_ERR_UNSUPPORTED, "W~ larger than 2^32 entries per handle");

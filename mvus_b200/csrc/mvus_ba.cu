@@ -239,6 +239,7 @@ static cudaError_t upload_segments(int device, const std::vector<UploadSeg>& seg
 // world size at the first solve.  Any later mvus_ba_set_detections / set_splines / comm_init must
 // make solver_alloc run again, or K2 and the cyclic-reduction levels would use stale block counts.
 void mvus::invalidate_solver(mvus_ba_ctx* h) {
+    h->chunk_sorted = false;
     if (h->solve_graph) { cudaGraphExecDestroy(h->solve_graph); h->solve_graph = nullptr; }
     if (h->graph_state > 0) h->graph_state = 0;
     if (h->st) cudaStreamSynchronize(h->st);      // (the handle's own stream is the only user of these)
@@ -435,8 +436,14 @@ int mvus::evaluate(mvus_ba_ctx* h, const double* xd, bool want_j) {
         h->sv, xd, h->camprep.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p,           \
         h->frame.p, h->xr.p, h->yr.p, h->obs_u.p, h->obs_v.p, h->desc.undist_points, h->desc.opt_sync,  \
         h->desc.opt_rs, h->N, h->r.p, h->J.p, h->partial.p)
-        if (h->desc.opt_calib) { if (want_j) MV_LAUNCH_K1(true, true); else MV_LAUNCH_K1(true, false); }
-        else { if (want_j) MV_LAUNCH_K1(false, true); else MV_LAUNCH_K1(false, false); }
+#define MV_LAUNCH_R2(CAL)                                                                               \
+    residual2_kernel<CAL><<<(h->n_tiles + 1) / 2, TILE_DET, 0, h->st>>>(                                \
+        h->sv, xd, h->camprep.p, h->tile_cam.p, h->tile_start.p, h->tile_cnt.p, h->row_off.p,           \
+        h->frame.p, h->xr.p, h->yr.p, h->obs_u.p, h->obs_v.p, h->desc.undist_points, h->desc.opt_sync,  \
+        h->desc.opt_rs, h->n_tiles, h->r.p, h->partial.p)
+        if (h->desc.opt_calib) { if (want_j) MV_LAUNCH_K1(true, true); else MV_LAUNCH_R2(true); }
+        else { if (want_j) MV_LAUNCH_K1(false, true); else MV_LAUNCH_R2(false); }
+#undef MV_LAUNCH_R2
 #undef MV_LAUNCH_K1
         h->launches++;
     }
@@ -620,6 +627,7 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
     mvus_ba_stats st;
     memset(&st, 0, sizeof(st));
     h->launches = 0;
+    h->chunk_sorted = false;
     h->ms_syrk = h->ms_bcr = h->ms_reduce = h->ms_k2 = 0.0;
     const double ftol = h->desc.ftol, xtol = h->desc.xtol, gtol = h->desc.gtol;
     const int max_nfev = h->desc.max_nfev > 0 ? h->desc.max_nfev : 100 * (int)std::min<int64_t>(h->n, 1000);
@@ -825,6 +833,7 @@ extern "C" int mvus_ba_normal_equations(mvus_ba_handle h, const double* x, doubl
     if (rc) return rc;
     rc = check_motion_flag(h);
     if (rc) return rc;
+    h->chunk_sorted = false;
     rc = accumulate(h);
     if (!rc) rc = reduce_normal_equations(h, true);      // diagnostics: every rank gets everything
     if (!rc) rc = compute_diag(h, true);
@@ -879,7 +888,8 @@ extern "C" int mvus_ba_time_accumulate(mvus_ba_handle h, int32_t reps, double* m
     if (!h->J.p) return fail(h, MVUS_ERR_ARG, "evaluate a Jacobian first (mvus_ba_time_resjac)");
     rc = ensure_solver(h);
     if (rc) return rc;
-    rc = accumulate(h);
+    h->chunk_sorted = false;
+    rc = accumulate(h);                  // (sorts the chunks; the timed repetitions reuse the order, as the LM loop does)
     if (rc) return rc;
     MV_CUDA(h, cudaEventRecord(h->ev[0], h->st));
     for (int k = 0; k < reps; ++k) {
