@@ -102,8 +102,9 @@ def test_solver_model_matches_dense_solve():
 
 
 def test_dropin_installs_on_the_reference_module():
-    """mvus_b200.dropin.install replaces Scene.BA (and the error_cam / remove_outliers satellites)
-    of the UNMODIFIED reference module with the same signatures."""
+    """mvus_b200.dropin.install replaces Scene.BA (and the error_cam / remove_outliers / traj_to_spline / align_gt
+    satellites) of the UNMODIFIED reference module with the same signatures, and uninstall puts every one of them
+    back."""
     import inspect
     from oracle import ref_shim
     if not ref_shim.available():
@@ -125,10 +126,18 @@ def test_dropin_installs_on_the_reference_module():
         fp_mir = FlatProblem(fl, fl.numCam, **bakw)
         assert np.abs(fp_ref.x0 - fp_mir.x0).max() <= 1e-12 * max(1.0, np.abs(fp_mir.x0).max())
         assert fp_ref.N == fp_mir.N and (fp_ref.knots == fp_mir.knots).all()
+        # the satellites either side of the BA: spline (re)fit and the ground-truth alignment main.py ends with
+        from analysis import compare_gt
+        assert common.Scene.traj_to_spline is not common.Scene._reference_traj_to_spline
+        assert compare_gt.align_gt is not compare_gt._reference_align_gt
+        assert list(inspect.signature(compare_gt.align_gt).parameters) == \
+            list(inspect.signature(compare_gt._reference_align_gt).parameters)
     finally:
-        common.Scene.BA = orig
-        common.Scene.error_cam = common.Scene._reference_error_cam
-        common.Scene.remove_outliers = common.Scene._reference_remove_outliers
+        dropin.uninstall(common)
+    from analysis import compare_gt
+    assert common.Scene.BA is orig and not hasattr(common.Scene, '_reference_BA')
+    assert not hasattr(common.Scene, '_reference_traj_to_spline') and not hasattr(compare_gt, '_reference_align_gt')
+    assert compare_gt.align_gt.__module__ == 'analysis.compare_gt'
 
 
 @pytest.mark.parametrize('name,scramble,bw', [('gs_plain', False, 3), ('rs_F_gap', False, 4), ('rs_F_gap', True, 3),
