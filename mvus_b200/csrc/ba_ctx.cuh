@@ -88,6 +88,7 @@ struct mvus_ba_ctx {
     int nc = 0, C = 6, Pc = 9, P = 21;
     int64_t N = 0, M = 0, n = 0, m = 0, n_other = 0, n_ctrl = 0;
     bool have_det = false, have_spl = false;
+    int motion_spread = 4;        // consecutive control points a motion-prior row touches (ba_tables.hpp)
 
     // detections
     std::vector<int64_t> cam_ptr;

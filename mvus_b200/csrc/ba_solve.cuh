@@ -781,27 +781,7 @@ __global__ void gradient_kernel(const double* __restrict__ bc, const double* __r
 // (reprojection rows touch 4 consecutive control points -> bw >= 3; a motion row touches up to `spread`
 // consecutive ones -> bw >= spread - 1), nb super-blocks, chunk size Bc of the sharded solve.
 inline int solver_dims(mvus_ba_ctx* h, int world, int* bw_out, int64_t* nb_out, int64_t* Bc_out) {
-    int spread = 4;
-    if (h->M > 0) {
-        std::vector<double> tau; std::vector<int> spl; std::vector<unsigned char> fl;
-        build_motion_samples(h->T, tau, spl, fl);
-        auto span_of = [&](int s, double t) {
-            const double* kn = h->T.knots.data() + h->T.knot_off[s];
-            const int k = h->T.deg[s], lmax = h->T.ncoef[s] - 1;
-            int lo = k, hi = lmax;
-            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (kn[mid] <= t) lo = mid; else hi = mid - 1; }
-            return lo;
-        };
-        for (size_t j = 0; j < tau.size(); ++j) {
-            if (!(fl[j] & 1)) continue;
-            int lo = span_of(spl[j], tau[j]), hi = lo;
-            if (fl[j] & 2) { const int l = span_of(spl[j], tau[j - 1]); lo = std::min(lo, l); hi = std::max(hi, l); }
-            if ((fl[j] & 4) && h->desc.motion_type == MVUS_MOTION_F) {
-                const int l = span_of(spl[j], tau[j + 1]); lo = std::min(lo, l); hi = std::max(hi, l);
-            }
-            spread = std::max(spread, hi - lo + 4);
-        }
-    }
+    const int spread = h->M > 0 ? h->motion_spread : 4;      // computed once in mvus_ba_set_splines (ba_tables.hpp)
     if (spread > 7) return fail(h, MVUS_ERR_UNSUPPORTED,
                                 "a motion-prior row touches more than 7 consecutive control points");
     const int bw = std::max(3, spread - 1);

@@ -10,7 +10,9 @@
 //              its span in O(1) instead of a bisection over up to 2e5 knots.
 #pragma once
 #include <stdint.h>
+#include <algorithm>
 #include <cmath>
+#include <thread>
 #include <vector>
 
 namespace mvus {
@@ -106,18 +108,30 @@ inline bool build_spline_tables(int S, const double* interval, const int64_t* kn
     for (int s = 0; s < S; ++s) {
         const double* U = knots + knot_ptr[s];
         const int k = T.deg[s], nco = T.ncoef[s];
-        for (int l = k; l <= nco - 1; ++l) {
-            const int64_t g = T.ctrl_off[s] + l;
-            T.span_t0[g] = U[l];
-            if (!(U[l + 1] > U[l])) continue;      // empty span: never selected
-            double ders[4][4];
-            basis_ders(U, l, k, U[l], ders);
-            double fact = 1.0;
-            for (int d = 0; d <= k; ++d) {
-                if (d > 0) fact *= d;
-                for (int m = 0; m <= k; ++m)          // basis (l-k+m) -> slot (3-k+m)
-                    T.spanpoly[(size_t)g * 16 + (3 - k + m) * 4 + d] = ders[d][m] / fact;
+        // (200 000 spans at config 4: 57 ms on one host core, inside every Scene.BA call -> split over threads)
+        auto span_range = [&](int l0, int l1) {
+            for (int l = l0; l < l1; ++l) {
+                const int64_t g = T.ctrl_off[s] + l;
+                T.span_t0[g] = U[l];
+                if (!(U[l + 1] > U[l])) continue;      // empty span: never selected
+                double ders[4][4];
+                basis_ders(U, l, k, U[l], ders);
+                double fact = 1.0;
+                for (int d = 0; d <= k; ++d) {
+                    if (d > 0) fact *= d;
+                    for (int m = 0; m <= k; ++m)          // basis (l-k+m) -> slot (3-k+m)
+                        T.spanpoly[(size_t)g * 16 + (3 - k + m) * 4 + d] = ders[d][m] / fact;
+                }
             }
+        };
+        const int nsp = nco - k;
+        const int nthr = nsp >= 32768 ? (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())) : 1;
+        if (nthr <= 1) span_range(k, nco);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nthr; ++t)
+                th.emplace_back(span_range, k + (int)((int64_t)nsp * t / nthr), k + (int)((int64_t)nsp * (t + 1) / nthr));
+            for (auto& x : th) x.join();
         }
         // lookup table: ~2 buckets per span
         const int nspans = nco - k;
@@ -150,6 +164,7 @@ inline void build_motion_samples(const HostSplineTables& T, std::vector<double>&
     const double start = T.int_a[0], stop = T.int_b[T.S - 1];
     const int64_t cnt = (int64_t)std::ceil((stop - start) / 1.0);
     std::vector<int> member;
+    tau.reserve((size_t)cnt + 2); spl.reserve((size_t)cnt + 2); member.reserve((size_t)cnt + 2);
     for (int s = 0; s < T.S; ++s) {
         int64_t i0 = (int64_t)std::floor(T.int_a[s] - start) - 1, i1 = (int64_t)std::ceil(T.int_b[s] - start) + 1;
         if (i0 < 0) i0 = 0;
@@ -178,6 +193,36 @@ inline void build_motion_samples(const HostSplineTables& T, std::vector<double>&
         if (j + 1 < M && member[j + 1] == member[j]) f |= 4;
         flags[j] = f;
     }
+}
+
+// Largest number of consecutive control points a motion-prior row touches (4 = one sample's support): the rows
+// of sample j involve the samples j-1 (KE, F) and j+1 (F) of the same group.  The samples are ascending inside a
+// spline, so the knot span follows by walking forward (a bisection per sample over 2e5 knots was 140 ms at
+// config 4 -- host time inside every Scene.BA call).
+inline int motion_spread(const HostSplineTables& T, const std::vector<double>& tau, const std::vector<int>& spl,
+                         const std::vector<unsigned char>& fl, bool least_force) {
+    const size_t M = tau.size();
+    std::vector<int> span(M, 0);
+    int cur_s = -1, l = 0;
+    double last_t = 0.0;
+    for (size_t j = 0; j < M; ++j) {
+        const int s = spl[j];
+        const double* kn = T.knots.data() + T.knot_off[s];
+        const int k = T.deg[s], lmax = T.ncoef[s] - 1;
+        if (s != cur_s || tau[j] < last_t) { cur_s = s; l = k; }
+        while (l < lmax && kn[l + 1] <= tau[j]) ++l;
+        span[j] = l;
+        last_t = tau[j];
+    }
+    int spread = 4;
+    for (size_t j = 0; j < M; ++j) {
+        if (!(fl[j] & 1)) continue;
+        int lo = span[j], hi = lo;
+        if (fl[j] & 2) { lo = std::min(lo, span[j - 1]); hi = std::max(hi, span[j - 1]); }
+        if ((fl[j] & 4) && least_force) { lo = std::min(lo, span[j + 1]); hi = std::max(hi, span[j + 1]); }
+        spread = std::max(spread, hi - lo + 4);
+    }
+    return spread;
 }
 
 }  // namespace mvus

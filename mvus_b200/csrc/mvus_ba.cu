@@ -389,12 +389,14 @@ extern "C" int mvus_ba_set_splines(mvus_ba_handle h, int32_t S, const double* in
                        h->ctrl_off.p, h->xoff.p, h->spanpoly.p, h->span_t0.p, h->lut_off.p, h->lut_n.p,
                        h->lut_t0.p, h->lut_invh.p, h->lut.p};
     h->M = 0;
+    h->motion_spread = 4;
     if (h->desc.motion_type != MVUS_MOTION_NONE) {
         std::vector<double> tau;
         std::vector<int> spl;
         std::vector<unsigned char> fl;
         build_motion_samples(T, tau, spl, fl);
         h->M = (int64_t)tau.size();
+        h->motion_spread = motion_spread(T, tau, spl, fl, h->desc.motion_type == MVUS_MOTION_F);
         MV_CUDA(h, upload(h->tau, tau, h->st));
         MV_CUDA(h, upload(h->tau_spl, spl, h->st));
         MV_CUDA(h, upload(h->tau_flag, fl, h->st));
