@@ -764,10 +764,7 @@ extern "C" int mvus_ba_solve(mvus_ba_handle h, const double* x0, double* x_out, 
         const double ratio = (pred > 0.0 && std::isfinite(Fn)) ? actual / pred : -1.0;
         if (verbose) fprintf(stderr, "[mvus_ba] nfev %d F %.8e Fn %.8e ratio %.3f lam %.3e |d|_D %.3e Delta %.3e |g|inf %.3e\n",
                              st.nfev, F, Fn, ratio, lam, nrm, Delta, st.optimality);
-        // (a step that INCREASES the cost by more than it promised to decrease it says the model is useless at this
-        //  radius: shrink by 10 like MINPACK's lmder does in that case, not by 4)
-        if (ratio < -1.0) Delta = 0.1 * nrm;
-        else if (ratio < 0.25) Delta = 0.25 * nrm;
+        if (ratio < 0.25) Delta = 0.25 * nrm;
         else if (ratio > 0.75 && nrm > 0.7 * Delta) Delta *= 2.0;
         const bool x_small = step_norm < xtol * (xtol + x_norm);
         if (std::isfinite(Fn) && actual > 0.0) {

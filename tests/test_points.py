@@ -100,7 +100,7 @@ def test_scene_ba_motion_prior_mode(case, built_lib, capsys):
     # against the reference's own 10-evaluation solve: on the least-force flights SciPy's TRF does not move at all
     # (cost = cost0, finite differences on the truncated pattern) and the GPU solve ends far below; on the
     # kinetic-energy flight TRF's 2-D subspace steps are the better match for the quartic valley and reach 263
-    # where the LM / trust-region driver is at 390 after the same 10 evaluations -- hence a one-sided
+    # where the LM / trust-region driver is at 505 after the same 10 evaluations -- hence a one-sided
     # bound where the reference stalls and a progress bound (>= 98 % of the way) where it does not
     cost0 = pp.cost(pp.x0)
     if gold['shipped_cost'] > 0.5 * cost0:
