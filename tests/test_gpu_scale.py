@@ -108,3 +108,18 @@ def test_full_size_solve_against_oracle_cost(built_lib):
     assert abs(prob.cost(x) - st.cost) <= 1e-9 * st.cost
     assert np.abs(prob.residual(x) - r).max() <= RTOL * np.abs(r).max()
     assert st.cost < 0.2 * prob.cost(prob.x0)
+
+
+@pytest.mark.gpu
+def test_bench_sample_cost_not_above_the_reference(built_lib):
+    """The 7-camera x 3000-detection sample bench.py runs on both arms (rolling shutter, distortion, least-force
+    prior with w = 1e4): after the reference's 10 evaluations the GPU cost must not be above what the UNMODIFIED
+    reference reaches from the same start (166 654.118: `bench.py --impl reference`, oracle/_ref, recorded in
+    profiles/r2_bench_n1_cfg4.json under cpu_baseline.final_cost; measured on the GPU: 58 187.6).  Guards the
+    trust-region rules of the LM driver: a stronger radius shrink once made this 305 940."""
+    import types
+    import bench
+    fl = bench.sample_flight(types.SimpleNamespace(sample_cams=7, sample_det=3000))
+    res = fl.BA(fl.numCam, max_iter=10, **bench.BA_KW)
+    assert res.nfev <= 10
+    assert res.cost <= 166654.11801197444 * (1 + 1e-6), res.cost
