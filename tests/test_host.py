@@ -101,6 +101,57 @@ def test_solver_model_matches_dense_solve():
         assert np.abs(mine - ref).max() <= 1e-8 * np.abs(ref).max()
 
 
+def test_chunk_prereduction_model_matches_dense_solve():
+    """tests/proto/bcr_proto.py::solve_chunked (the NumPy model csrc/ba_chunk.cuh mirrors: sequential elimination
+    inside chunks, head system, back substitution) == dense solve of the damped normal equations, for chunk
+    lengths that divide the block count, ragged ones and one chunk spanning everything; plus a larger random
+    block-tridiagonal system against the cyclic-reduction model."""
+    from proto import bcr_proto
+    from oracle import ba_oracle
+    for bw, name in ((3, 'gs_plain'), (4, 'rs_F_gap'), (6, 'rs_bounds_dense')):
+        fl, truth, bakw = cases.make(name, det_per_cam=150)
+        prob = ba_oracle.Problem(fl, fl.numCam, **bakw)
+        J = prob.jacobian(prob.x0).toarray() * prob.free_mask()[None, :]
+        r = prob.residual(prob.x0)
+        n_ctrl = sum(prob.ncoef)
+        cols = np.zeros((n_ctrl, 3), int)
+        j = 0
+        for s in range(prob.S):
+            for l in range(prob.ncoef[s]):
+                for ax in range(3):
+                    cols[j, ax] = prob.coef_off[s] + ax * prob.ncoef[s] + l
+                j += 1
+        A, bc, D, E, Wt, perm = bcr_proto.assemble(J, r, prob.n_other, n_ctrl, cols, bw)
+        lam = 1e-3
+        H = J.T @ J
+        ref = np.linalg.solve(H + lam * np.diag(np.clip(np.diag(H), 1e-6, 1e32)), -J.T @ r)
+        for Lc in (1, 2, 5, 64):
+            dc, ds = bcr_proto.solve_chunked(A, bc, D, E, Wt, lam, Lc)
+            mine = np.zeros(prob.n)
+            mine[:prob.n_other] = dc
+            flat = ds.reshape(-1)
+            ok = perm >= 0
+            mine[perm[ok]] = flat[ok]
+            assert np.abs(mine - ref).max() <= 1e-8 * np.abs(ref).max(), (name, Lc)
+    rng = np.random.default_rng(0)
+    for nb, q, ncp, Lc in ((37, 9, 12, 8), (65, 12, 7, 32), (5, 9, 4, 8)):
+        D = np.zeros((nb, q, q)); E = np.zeros((nb, q, q))
+        for k in range(nb):
+            Jb = rng.normal(size=(4 * q, 2 * q))
+            Hb = Jb.T @ Jb
+            D[k] += Hb[:q, :q]
+            if k + 1 < nb:
+                D[k + 1] += Hb[q:, q:]
+                E[k] += Hb[:q, q:]
+        Wt = rng.normal(size=(nb, q, ncp + 1))
+        A = np.eye(ncp) * 1e3 * q * nb
+        bc = rng.normal(size=ncp)
+        dc0, ds0 = bcr_proto.solve_bcr(A, bc, D, E, Wt, 1e-2)
+        dc1, ds1 = bcr_proto.solve_chunked(A, bc, D, E, Wt, 1e-2, Lc)
+        assert np.abs(dc0 - dc1).max() <= 1e-12 * np.abs(dc0).max()
+        assert np.abs(ds0 - ds1).max() <= 1e-12 * np.abs(ds0).max()
+
+
 def test_dropin_installs_on_the_reference_module():
     """mvus_b200.dropin.install replaces Scene.BA (and the error_cam / remove_outliers / traj_to_spline / align_gt
     satellites) of the UNMODIFIED reference module with the same signatures, and uninstall puts every one of them
